@@ -1,0 +1,1 @@
+"""alias package, see efa_xray/__init__.py"""

@@ -1,0 +1,1 @@
+from efa_xray_b200.assimilation.assimilation import Assimilation, update, ObTimeOutsideState  # noqa: F401

@@ -1,0 +1,241 @@
+// Library plumbing (errors, device check), the FP64-pipe peak probe and the host-buffer entry point
+// that strings the kernels together the way EnSRF.update() does (assimilation/ensrf.py:33-151).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <cmath>
+
+static thread_local char g_err[512] = "";
+
+void exb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int exb_check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        exb_set_error("%s: launch failed -> %s", what, cudaGetErrorString(e));
+        return EXB_ERR_CUDA;
+    }
+    return EXB_OK;
+}
+
+extern "C" int exb_version(void) { return 100; }
+extern "C" const char *exb_last_error(void) { return g_err; }
+
+extern "C" int exb_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        exb_set_error("exb_device_check: no CUDA device -> %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return EXB_ERR_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    EXB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        exb_set_error("exb_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                      prop.major, prop.minor);
+        return EXB_ERR_NODEVICE;
+    }
+    return EXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 FMA peak probe
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+        c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+    }
+    const double r = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+    if (r == 123.456) out[0] = r;      // never true; keeps the loop alive
+}
+
+extern "C" int exb_measure_fp64_peak(double *tflops, void *stream) {
+    EXB_REQUIRE(tflops, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *out = nullptr;
+    EXB_CUDA(cudaMalloc(&out, sizeof(double)));
+    const int iters = 1 << 15, blocks = 148 * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    EXB_CUDA(cudaEventCreate(&e0));
+    EXB_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        EXB_CUDA(cudaEventRecord(e0, st));
+        fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+        EXB_CUDA(cudaEventRecord(e1, st));
+        EXB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        EXB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return exb_check_launch("fp64_peak_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// whole analysis with host buffers
+// ------------------------------------------------------------------------------------------
+// 8-point stencil = 4 space points x 2 time levels, weights multiplied (state/ensemble.py:226-237)
+__global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *__restrict__ w4,
+                                const int64_t *__restrict__ row0, const int64_t *__restrict__ row1,
+                                const double *__restrict__ tw0, const double *__restrict__ tw1, int64_t nobs,
+                                int64_t *__restrict__ idx8, double *__restrict__ w8) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nobs) return;
+    for (int p = 0; p < 4; ++p) {
+        idx8[k * 8 + p] = row0[k] + idx4[k * 4 + p];
+        w8[k * 8 + p] = tw0[k] * w4[k * 4 + p];
+        idx8[k * 8 + 4 + p] = row1[k] + idx4[k * 4 + p];
+        w8[k * 8 + 4 + p] = tw1[k] * w4[k * 4 + p];
+    }
+}
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+}   // namespace
+
+#define EXB_TRY(call)              \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != EXB_OK) return rc__; \
+    } while (0)
+
+extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                                  const double *lat_deg, const double *lon_deg, int64_t nobs,
+                                  const double *ob_value, const double *ob_error, const double *ob_lat_deg,
+                                  const double *ob_lon_deg, const double *ob_halfwidth_km,
+                                  const uint8_t *ob_assimilate, const int64_t *ob_row0, const int64_t *ob_row1,
+                                  const double *ob_tw0, const double *ob_tw1, int loc_mode, double inflation,
+                                  double *ob_diag, double *stats) {
+    EXB_REQUIRE(X_host && lat_deg && lon_deg && ob_value && ob_error && ob_lat_deg && ob_lon_deg && ob_assimilate &&
+                    ob_row0 && ob_row1 && ob_tw0 && ob_tw1 && ob_diag, "null pointer");
+    EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nens >= 2 && nobs > 0, "bad sizes");
+    EXB_TRY(exb_device_check());
+    const int64_t npts = ny * nx, nrows = nlev * npts;
+    cudaStream_t st = nullptr;
+    EXB_CUDA(cudaStreamCreate(&st));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sguard{st};
+    cudaEvent_t ev[5];
+    for (auto &e : ev) EXB_CUDA(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); } } eguard{ev};
+
+    DevBuf dX, dxm, dlat, dlon, dgu, dsl, dcl, dob, dassim, drow, dtw, dgeo, didx4, dw4, didx8, dw8, dY, dYm, drec, dcnt, dnex;
+    EXB_CUDA(dX.alloc((size_t)nrows * nens * sizeof(double)));
+    EXB_CUDA(dxm.alloc((size_t)nrows * sizeof(double)));
+    EXB_CUDA(dlat.alloc(npts * sizeof(double)));
+    EXB_CUDA(dlon.alloc(npts * sizeof(double)));
+    EXB_CUDA(dgu.alloc(3 * npts * sizeof(double)));
+    EXB_CUDA(dsl.alloc(npts * sizeof(double)));
+    EXB_CUDA(dcl.alloc(npts * sizeof(double)));
+    EXB_CUDA(dob.alloc(7 * nobs * sizeof(double)));      // value error lat lon hw sinlat coslon
+    EXB_CUDA(dassim.alloc(nobs));
+    EXB_CUDA(drow.alloc(2 * nobs * sizeof(int64_t)));
+    EXB_CUDA(dtw.alloc(2 * nobs * sizeof(double)));
+    EXB_CUDA(dgeo.alloc(EXB_GEO_FIELDS * nobs * sizeof(double)));
+    EXB_CUDA(didx4.alloc(4 * nobs * sizeof(int64_t)));
+    EXB_CUDA(dw4.alloc(4 * nobs * sizeof(double)));
+    EXB_CUDA(didx8.alloc(8 * nobs * sizeof(int64_t)));
+    EXB_CUDA(dw8.alloc(8 * nobs * sizeof(double)));
+    EXB_CUDA(dY.alloc((size_t)nobs * nens * sizeof(double)));
+    EXB_CUDA(dYm.alloc(nobs * sizeof(double)));
+    EXB_CUDA(drec.alloc(EXB_REC_FIELDS * nobs * sizeof(double)));
+    EXB_CUDA(dcnt.alloc(2 * sizeof(unsigned long long)));
+    EXB_CUDA(dnex.alloc(sizeof(int32_t)));
+
+    // host-side tables of the pseudo-metric (state/ensemble.py:160-163)
+    std::vector<double> sl(npts), cl(npts), osl(nobs), ocl(nobs);
+    for (int64_t i = 0; i < npts; ++i) { sl[i] = sin(lat_deg[i] * EXB_DEG2RAD); cl[i] = cos(lon_deg[i] * EXB_DEG2RAD); }
+    for (int64_t k = 0; k < nobs; ++k) { osl[k] = sin(ob_lat_deg[k] * EXB_DEG2RAD); ocl[k] = cos(ob_lon_deg[k] * EXB_DEG2RAD); }
+
+    double *ob = dob.as<double>();
+    EXB_CUDA(cudaEventRecord(ev[0], st));
+    EXB_CUDA(cudaMemcpyAsync(dX.p, X_host, (size_t)nrows * nens * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaEventRecord(ev[1], st));
+    EXB_CUDA(cudaMemcpyAsync(dlat.p, lat_deg, npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dlon.p, lon_deg, npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dsl.p, sl.data(), npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dcl.p, cl.data(), npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(ob + 0 * nobs, ob_value, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(ob + 1 * nobs, ob_error, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(ob + 2 * nobs, ob_lat_deg, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(ob + 3 * nobs, ob_lon_deg, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (loc_mode == EXB_LOC_GC) {
+        EXB_REQUIRE(ob_halfwidth_km, "loc_mode GC needs halfwidths");
+        EXB_CUDA(cudaMemcpyAsync(ob + 4 * nobs, ob_halfwidth_km, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    EXB_CUDA(cudaMemcpyAsync(ob + 5 * nobs, osl.data(), nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(ob + 6 * nobs, ocl.data(), nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dassim.p, ob_assimilate, nobs, cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(drow.p, ob_row0, nobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(drow.as<int64_t>() + nobs, ob_row1, nobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dtw.p, ob_tw0, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dtw.as<double>() + nobs, ob_tw1, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemsetAsync(dcnt.p, 0, 2 * sizeof(unsigned long long), st));
+
+    // setup: inflation, geometry, forward operator, mean/perturbation split
+    if (inflation != 1.0) EXB_TRY(exb_inflate_f64(dX.as<double>(), nrows, nens, &inflation, 1, nrows, st));
+    EXB_TRY(exb_grid_unitvec(dlat.as<double>(), dlon.as<double>(), npts, dgu.as<double>(), st));
+    EXB_TRY(exb_obs_prepare(ob + 2 * nobs, ob + 3 * nobs, ob + 4 * nobs, nobs, loc_mode, dgeo.as<double>(), st));
+    EXB_TRY(exb_stencil_search(dsl.as<double>(), dcl.as<double>(), dlat.as<double>(), dlon.as<double>(), npts,
+                               ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs, didx4.as<int64_t>(),
+                               dw4.as<double>(), dnex.as<int32_t>(), st));
+    stencil8_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(didx4.as<int64_t>(), dw4.as<double>(),
+                                                                     drow.as<int64_t>(), drow.as<int64_t>() + nobs,
+                                                                     dtw.as<double>(), dtw.as<double>() + nobs, nobs,
+                                                                     didx8.as<int64_t>(), dw8.as<double>());
+    EXB_TRY(exb_check_launch("stencil8_kernel"));
+    EXB_TRY(exb_gather_f64(dX.as<double>(), nrows, nens, didx8.as<int64_t>(), dw8.as<double>(), 8, nobs,
+                           dY.as<double>(), st));
+    EXB_TRY(exb_split_mean_pert_f64(dY.as<double>(), dYm.as<double>(), nobs, nens, st));
+    EXB_TRY(exb_split_mean_pert_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
+    EXB_CUDA(cudaEventRecord(ev[2], st));
+
+    // the serial analysis
+    EXB_TRY(exb_obs_solve_f64(dYm.as<double>(), dY.as<double>(), ob + 0 * nobs, ob + 1 * nobs, dassim.as<uint8_t>(),
+                              dgeo.as<double>(), nobs, nens, loc_mode, drec.as<double>(),
+                              dcnt.as<unsigned long long>(), st));
+    EXB_TRY(exb_state_update_f64(dxm.as<double>(), dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(),
+                                 dY.as<double>(), drec.as<double>(), dgeo.as<double>(), nobs, 0, nobs, loc_mode,
+                                 dcnt.as<unsigned long long>(), st));
+    EXB_TRY(exb_recombine_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
+    EXB_CUDA(cudaEventRecord(ev[3], st));
+
+    EXB_CUDA(cudaMemcpyAsync(X_host, dX.p, (size_t)nrows * nens * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EXB_CUDA(cudaMemcpyAsync(ob_diag, drec.p, 4 * nobs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EXB_CUDA(cudaEventRecord(ev[4], st));
+    unsigned long long cnt[2] = {0, 0};
+    int32_t nex = 0;
+    EXB_CUDA(cudaMemcpyAsync(cnt, dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    EXB_CUDA(cudaMemcpyAsync(&nex, dnex.p, sizeof(nex), cudaMemcpyDeviceToHost, st));
+    EXB_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms[4];
+        for (int i = 0; i < 4; ++i) EXB_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        stats[0] = (double)cnt[1] * (double)nlev;
+        stats[1] = (double)cnt[0];
+        stats[2] = (double)nex;
+        for (int i = 0; i < 4; ++i) stats[3 + i] = ms[i];
+        stats[7] = 0.0;
+    }
+    return EXB_OK;
+}

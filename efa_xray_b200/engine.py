@@ -1,0 +1,274 @@
+"""Array-level driver of the serial EnSRF analysis on B200.
+
+This is the host side between the reference-shaped Python API (efa_xray_b200.assimilation) and the C ABI
+(include/efa_xray_b200.h).  torch is used for device memory, streams, events and (multi-GPU)
+torch.distributed only; every arithmetic step is a kernel of libefa_xray_b200.
+
+Sequence (reference: assimilation/ensrf.py:33-151, assimilation/assimilation.py:120-171):
+    upload  ->  [inflate]  ->  ob priors H.x  ->  mean/perturbation split  ->  obs-space serial solve
+            ->  state sweep (per latitude band)  ->  recombine  ->  download
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+LOC_NONE, LOC_GC = 0, 1
+
+
+@dataclass
+class ObsArrays:
+    """Structure-of-arrays view of a list of Observation objects (observation/observation.py:18-36)."""
+    value: np.ndarray
+    error: np.ndarray            # variance
+    lat: np.ndarray
+    lon: np.ndarray
+    halfwidth: np.ndarray        # km; ignored when loc_mode == LOC_NONE
+    assimilate: np.ndarray       # uint8
+    row0: np.ndarray             # first state row of (variable, lower time level)
+    row1: np.ndarray             # first state row of (variable, upper time level)
+    tw0: np.ndarray              # time weights of the two levels (state/ensemble.py:202-224)
+    tw1: np.ndarray
+
+    @property
+    def nobs(self):
+        return int(self.value.shape[0])
+
+
+@dataclass
+class AnalysisResult:
+    prior_mean: np.ndarray
+    prior_var: np.ndarray
+    post_mean: np.ndarray        # NaN where the ob was not assimilated
+    post_var: np.ndarray
+    assimilated: np.ndarray      # bool
+    n_exact: int = 0             # obs within 1 km of a selected grid point
+    state_pairs: int = 0         # sum_k |F_s(k)|   (state rows with non-zero weight, all levels)
+    obs_pairs: int = 0           # sum_k |F_o(k)|
+    ms: dict = field(default_factory=dict)
+
+
+def time_weights(valid_times, ob_times):
+    """Vectorised restatement of the time-weight logic of EnsembleState.interpolate
+    (state/ensemble.py:202-224), including its swapped linear weights.  Returns
+    (tlo, thi, wlo, whi, outside) with weights attached to time indices tlo = lastdex-1, thi = lastdex."""
+    valids = np.asarray(valid_times).astype('datetime64[ns]')
+    t = np.asarray(ob_times).astype('datetime64[ns]')
+    outside = (t < valids[0]) | (t > valids[-1])
+    lastdex = np.searchsorted(valids, t, side='left')            # first index with valids >= t
+    lastdex = np.clip(lastdex, 0, len(valids) - 1)
+    exact = valids[lastdex] == t
+    lo = np.maximum(lastdex - 1, 0)
+    totsec = np.abs((valids[lastdex] - valids[lo]) / np.timedelta64(1, 's'))
+    thissec = np.abs((t - valids[lastdex]) / np.timedelta64(1, 's'))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        frac = thissec.astype(np.float64) / totsec
+    whi = np.where(exact, 1.0, frac)                              # timeweights[lastdex]
+    wlo = np.where(exact, 0.0, 1.0 - frac)                        # timeweights[lastdex-1]
+    return lo.astype(np.int64), lastdex.astype(np.int64), wlo, whi, outside
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev_f64(a, device):
+    torch = _torch()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+class GridTables:
+    """Device-resident geometry of the (ny, nx) grid: lat/lon, the pseudo-metric tables of
+    nearest_points (state/ensemble.py:160-163, computed with numpy so that ties fall where they do on the
+    host) and unit vectors for great-circle distances."""
+
+    def __init__(self, lat2d, lon2d, device):
+        torch = _torch()
+        lat2d = np.ascontiguousarray(lat2d, dtype=np.float64)
+        lon2d = np.ascontiguousarray(lon2d, dtype=np.float64)
+        assert lat2d.ndim == 2 and lat2d.shape == lon2d.shape, '2-D lat(y,x)/lon(y,x) required'
+        self.ny, self.nx = lat2d.shape
+        self.npts = self.ny * self.nx
+        self.device = device
+        self.lat = _dev_f64(lat2d.ravel(), device)
+        self.lon = _dev_f64(lon2d.ravel(), device)
+        self.sinlat = _dev_f64(np.sin(np.radians(lat2d)).ravel(), device)
+        self.coslon = _dev_f64(np.cos(np.radians(lon2d)).ravel(), device)
+        self.u = torch.empty((3, self.npts), dtype=torch.float64, device=device)
+        _lib.call('exb_grid_unitvec', _lib.ptr(self.lat), _lib.ptr(self.lon), self.npts, _lib.ptr(self.u),
+                  _lib.stream_ptr())
+
+
+def stencil_search(grid: GridTables, ob_lat, ob_lon):
+    """4 nearest points (pseudo-metric) and inverse-distance weights for every ob -> device tensors
+    idx4 [nobs,4] int64, w4 [nobs,4] float64, and the number of obs within 1 km of a selected point."""
+    torch = _torch()
+    dev = grid.device
+    ob_lat = np.ascontiguousarray(ob_lat, dtype=np.float64)
+    ob_lon = np.ascontiguousarray(ob_lon, dtype=np.float64)
+    nobs = ob_lat.shape[0]
+    d_lat, d_lon = _dev_f64(ob_lat, dev), _dev_f64(ob_lon, dev)
+    d_sl = _dev_f64(np.sin(np.radians(ob_lat)), dev)
+    d_cl = _dev_f64(np.cos(np.radians(ob_lon)), dev)
+    idx4 = torch.empty((nobs, 4), dtype=torch.int64, device=dev)
+    w4 = torch.empty((nobs, 4), dtype=torch.float64, device=dev)
+    nex = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call('exb_stencil_search', _lib.ptr(grid.sinlat), _lib.ptr(grid.coslon), _lib.ptr(grid.lat),
+              _lib.ptr(grid.lon), grid.npts, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat), _lib.ptr(d_lon),
+              nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
+    return idx4, w4, nex
+
+
+def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx):
+    """Y[nobs, nens] = H X for all obs (compute_ob_priors, assimilation/assimilation.py:36-49)."""
+    torch = _torch()
+    dev = X.device
+    idx4, w4, nex = stencil_search(grid, obs.lat, obs.lon)
+    row0 = torch.as_tensor(obs.row0).to(dev)
+    row1 = torch.as_tensor(obs.row1).to(dev)
+    tw0, tw1 = _dev_f64(obs.tw0, dev), _dev_f64(obs.tw1, dev)
+    # 8-point stencil = 4 space points x 2 time levels (index/weight bookkeeping only)
+    idx8 = torch.cat([row0[:, None] + idx4, row1[:, None] + idx4], dim=1).contiguous()
+    w8 = torch.cat([tw0[:, None] * w4, tw1[:, None] * w4], dim=1).contiguous()
+    Y = torch.empty((obs.nobs, X.shape[1]), dtype=X.dtype, device=dev)
+    _lib.call('exb_gather_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(idx8), _lib.ptr(w8), 8,
+              obs.nobs, _lib.ptr(Y), _lib.stream_ptr())
+    return Y, nex
+
+
+def _sfx(dtype):
+    torch = _torch()
+    if dtype == torch.float64:
+        return 'f64'
+    if dtype == torch.float32:
+        return 'f32'
+    raise TypeError('efa_xray_b200 supports float64 and float32 states, got %r' % (dtype,))
+
+
+class _Timer:
+    def __init__(self, enabled=True):
+        self.torch = _torch()
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if not self.enabled or not self.marks:
+            return {}
+        self.torch.cuda.synchronize()
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx):
+    _lib.call('exb_obs_solve_' + sfx, _lib.ptr(Ym), _lib.ptr(Yp), _lib.ptr(obs_dev['value']),
+              _lib.ptr(obs_dev['error']), _lib.ptr(obs_dev['assimilate']), _lib.ptr(geo), Ym.shape[0], nens,
+              loc_mode, _lib.ptr(rec), _lib.ptr(counters), _lib.stream_ptr())
+
+
+def state_update(xm, Xp, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, counters, sfx, ob_begin=0, ob_end=None):
+    _lib.call('exb_state_update_' + sfx, _lib.ptr(xm), _lib.ptr(Xp), nlev, ny, nx, Xp.shape[-1], _lib.ptr(grid_u),
+              _lib.ptr(Yp), _lib.ptr(rec), _lib.ptr(geo), nobs, ob_begin, nobs if ob_end is None else ob_end,
+              loc_mode, _lib.ptr(counters), _lib.stream_ptr())
+
+
+def upload_obs(obs: ObsArrays, device, loc_mode):
+    torch = _torch()
+    d = {
+        'value': _dev_f64(obs.value, device),
+        'error': _dev_f64(obs.error, device),
+        'lat': _dev_f64(obs.lat, device),
+        'lon': _dev_f64(obs.lon, device),
+        'assimilate': torch.as_tensor(np.ascontiguousarray(obs.assimilate, dtype=np.uint8)).to(device),
+    }
+    d['halfwidth'] = _dev_f64(obs.halfwidth, device) if loc_mode == LOC_GC else None
+    geo = torch.empty((8, obs.nobs), dtype=torch.float64, device=device)
+    _lib.call('exb_obs_prepare', _lib.ptr(d['lat']), _lib.ptr(d['lon']), _lib.ptr(d['halfwidth']), obs.nobs,
+              loc_mode, _lib.ptr(geo), _lib.stream_ptr())
+    return d, geo
+
+
+def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflation=None, timing=True):
+    """Serial EnSRF analysis of a device-resident ensemble, in place.
+
+    X        torch tensor [nlev*ny*nx, nens] (float64 or float32) on a CUDA device, to_vect layout
+             (state/ensemble.py:110-114); overwritten with the analysis ensemble.
+    inflation  None, or a numpy array of per-level multiplicative factors (length nlev).
+    Returns an AnalysisResult with the per-ob diagnostics of ensrf.py:66-70,144-149.
+    """
+    torch = _torch()
+    _lib.require_device()
+    sfx = _sfx(X.dtype)
+    dev = X.device
+    nrows, nens = X.shape
+    ny, nx = grid.ny, grid.nx
+    assert nrows == nlev * ny * nx, (nrows, nlev, ny, nx)
+    assert X.is_contiguous()
+    tm = _Timer(timing)
+    tm.mark('start')
+    with torch.cuda.device(dev):
+        if inflation is not None:
+            fac = np.ascontiguousarray(inflation, dtype=np.float64)
+            assert fac.shape == (nlev,)
+            _lib.call('exb_inflate_' + sfx, _lib.ptr(X), nrows, nens, fac.ctypes.data_as(C.c_void_p), nlev,
+                      ny * nx, _lib.stream_ptr())
+        obs_dev, geo = upload_obs(obs, dev, loc_mode)
+        Yp, nex = ob_priors(X, grid, obs, sfx)
+        Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
+        _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
+        xm = torch.empty(nrows, dtype=X.dtype, device=dev)
+        _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+        tm.mark('setup')
+        rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
+        counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx)
+        tm.mark('obs_solve')
+        state_update(xm, X, nlev, ny, nx, grid.u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
+        tm.mark('state_update')
+        _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+        tm.mark('recombine')
+        rec_h = rec.cpu().numpy()
+        cnt = counters.cpu().numpy()
+        nex_h = int(nex.item())
+    return AnalysisResult(prior_mean=rec_h[0], prior_var=rec_h[1], post_mean=rec_h[2], post_var=rec_h[3],
+                          assimilated=rec_h[7] != 0.0, n_exact=nex_h, state_pairs=int(cnt[1]) * nlev,
+                          obs_pairs=int(cnt[0]), ms=tm.result())
+
+
+def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflation=None, device='cuda:0',
+                  dtype=None, grid=None):
+    """Host-buffer entry: X_host is a numpy array or CPU torch tensor [nlev*ny*nx, nens]; it is uploaded,
+    analysed on `device` and written back in place.  Pinned host memory makes the copies asynchronous."""
+    torch = _torch()
+    _lib.require_device()
+    Xh = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(X_host)
+    assert Xh.is_contiguous()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev2 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.device(device):
+        ev0.record()
+        X = Xh.to(device, non_blocking=True)
+        if dtype is not None and X.dtype != dtype:
+            X = X.to(dtype)
+        ev1.record()
+        if grid is None:
+            grid = GridTables(lat2d, lon2d, torch.device(device))
+        res = analysis_device(X, nlev, grid, obs, loc_mode, inflation)
+        ev2.record()
+        Xh.copy_(X.to(Xh.dtype) if X.dtype != Xh.dtype else X)
+        torch.cuda.synchronize()
+        res.ms['upload'] = ev0.elapsed_time(ev1)
+    return res

@@ -1,0 +1,178 @@
+/*
+ * efa_xray_b200 -- C ABI of the B200 (sm_100a) serial-EnSRF analysis step.
+ *
+ * Drop-in boundary for the hot path of lmadaus/efa_xray: EnSRF(state, obs, loc='GC').update()
+ * (efa_xray/assimilation/ensrf.py:33-151).  The reference has no FFI of its own (it is pure Python
+ * on numpy), so these are the entry points a ctypes binding placed under its Python API calls; see
+ * INTEGRATION.md for the stub.  Citations below are file:line under /root/reference/efa_xray/.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - Every function returns 0 on success or a negative EXB_ERR_* code; exb_last_error() gives the
+ *     message for the calling thread.  Nothing throws across the boundary.
+ *   - Functions WITHOUT the _host suffix take DEVICE pointers (caller owns the memory, e.g. torch
+ *     tensors) and a cudaStream_t passed as void*; they only enqueue work on that stream.
+ *   - Functions WITH the _host suffix take HOST pointers, do their own H2D/D2H and synchronise.
+ *   - _f64 / _f32 select the storage+arithmetic type T of means and perturbations.  Per-observation
+ *     scalars (variance, innovation, gain denominator, beta) and all geometry are always double.
+ *   - State matrix layout is the reference's to_vect() layout (state/ensemble.py:110-114):
+ *     X[row][member], row = ((var*nt + t)*ny + y)*nx + x, member contiguous.  "nlev" = nvar*nt.
+ *   - Observation geometry "obgeo" is an SoA block double[8][nobs] made by exb_obs_prepare:
+ *     0..2 unit vector, 3 1/|halfwidth|, 4 haversine-a cutoff, 5 cos(theta), 6 sin(theta), 7 theta,
+ *     theta = support radius (2*|halfwidth|) as an angle, clamped to pi.
+ *   - Per-observation records "rec" are an SoA block double[8][nobs] written by exb_obs_solve_*:
+ *     0 prior_mean, 1 prior_var, 2 post_mean, 3 post_var (NaN if skipped), 4 innovation,
+ *     5 1/((Nens-1)*kdenom), 6 beta, 7 assimilated (1.0 / 0.0).
+ */
+#ifndef EFA_XRAY_B200_H
+#define EFA_XRAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXB_OK 0
+#define EXB_ERR_ARG (-1)        /* bad argument (null pointer, size out of range)            */
+#define EXB_ERR_CUDA (-2)       /* a CUDA runtime call or kernel launch failed               */
+#define EXB_ERR_UNSUPPORTED (-3)/* e.g. ensemble size above EXB_MAX_NENS                     */
+#define EXB_ERR_NODEVICE (-4)   /* no CUDA device / not an sm_100 device                     */
+
+#define EXB_MAX_NENS 256
+#define EXB_LOC_NONE 0          /* loc in (None, False): no localisation, ensrf.py:99        */
+#define EXB_LOC_GC 1            /* loc == 'GC': Gaspari-Cohn, observation.py:117-130          */
+#define EXB_REC_FIELDS 8
+#define EXB_GEO_FIELDS 8
+
+/* ---- library ---------------------------------------------------------------------------- */
+int exb_version(void);                       /* 100*major + minor                             */
+const char *exb_last_error(void);            /* message of the last failure on this thread    */
+int exb_device_check(void);                  /* 0 if the current device can run the kernels   */
+
+/* ---- geometry --------------------------------------------------------------------------- */
+/* Unit vectors of grid points from lat/lon in degrees; out is SoA double[3][npts].
+ * Feeds the on-the-fly great-circle distance that replaces EnsembleState.distance_to_point
+ * (state/ensemble.py:254-267). */
+int exb_grid_unitvec(const double *lat_deg, const double *lon_deg, int64_t npts, double *grid_u,
+                     void *stream);
+
+/* Per-observation geometry (see "obgeo" above) from lat/lon in degrees and the Gaspari-Cohn
+ * half-width in km (Observation.localize_radius, observation.py:62; abs() as observation.py:120).
+ * With loc_mode == EXB_LOC_NONE every weight is 1 and halfwidth may be NULL. */
+int exb_obs_prepare(const double *ob_lat_deg, const double *ob_lon_deg, const double *ob_halfwidth_km,
+                    int64_t nobs, int loc_mode, double *obgeo, void *stream);
+
+/* Distances (km) and localisation weights from ONE observation to n points given as unit vectors
+ * (SoA double[3][n], from exb_grid_unitvec): Observation.distance_to_state / Observation.localize for a
+ * state or a list of obs (observation/observation.py:53-87).  Either output may be NULL. */
+int exb_localization_weights(const double *u, int64_t n, double ob_lat_deg, double ob_lon_deg,
+                             double halfwidth_km, int loc_mode, double *dist_km, double *weights, void *stream);
+
+/* gaspari_cohn(distances, halfwidth), elementwise (observation/observation.py:117-130). */
+int exb_gaspari_cohn(const double *dist_km, int64_t n, double halfwidth_km, double *weights, void *stream);
+
+/* ---- forward operator: EnsembleState.nearest_points + interpolate ------------------------ */
+/* For every ob the 4 grid points with the smallest pseudo-distance
+ *   hypot(sin(lat_g) - sin(lat_ob), cos(lon_g) - cos(lon_ob))        (state/ensemble.py:160-165)
+ * ordered by (distance, flat index), then true haversine distances to them and inverse-distance
+ * weights (state/ensemble.py:181-200).  sinlat_g / coslon_g / ob_sinlat / ob_coslon are the caller's
+ * tables of sin(radians(lat)) and cos(radians(lon)) so that ties fall exactly where they do on the
+ * host.  idx4 is int64[nobs][4] (flat y*nx+x), w4 double[nobs][4].
+ * n_exact (device int32[1], may be NULL) counts obs with a selected point closer than 1 km, where the
+ * reference raises IndexError (state/ensemble.py:195-196); for those obs w4 is 1 at the nearest point
+ * and 0 elsewhere (what that branch was meant to do). */
+int exb_stencil_search(const double *sinlat_g, const double *coslon_g, const double *lat_g_deg,
+                       const double *lon_g_deg, int64_t npts, const double *ob_sinlat,
+                       const double *ob_coslon, const double *ob_lat_deg, const double *ob_lon_deg,
+                       int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream);
+
+/* Y[k][m] = sum_p w[k][p] * X[idx[k][p]][m], p < K (K <= 8): the gather + weighted sums of
+ * interpolate (state/ensemble.py:226-237) for all obs at once (compute_ob_priors,
+ * assimilation/assimilation.py:36-49).  idx are ROW indices into X. */
+int exb_gather_f64(const double *X, int64_t nrows, int nens, const int64_t *idx, const double *w, int K,
+                   int64_t nobs, double *Y, void *stream);
+int exb_gather_f32(const float *X, int64_t nrows, int nens, const int64_t *idx, const double *w, int K,
+                   int64_t nobs, float *Y, void *stream);
+
+/* In place: xm[r] = mean_m X[r][m]; X[r][m] -= xm[r]   (assimilation/assimilation.py:146-147 for the
+ * state, :47-48 for the ob priors). */
+int exb_split_mean_pert_f64(double *X, double *xm, int64_t nrows, int nens, void *stream);
+int exb_split_mean_pert_f32(float *X, float *xm, int64_t nrows, int nens, void *stream);
+
+/* In place multiplicative inflation about the ensemble mean, X = (X - mean)*factor + mean, the float
+ * path of inflate_state (assimilation/assimilation.py:62-69).  factor is per row block:
+ * rows [i*rows_per_factor, (i+1)*rows_per_factor) use factor[i] (host array of nfactor doubles), which
+ * covers both the single float and the per-variable dict (assimilation.py:103-114). */
+int exb_inflate_f64(double *X, int64_t nrows, int nens, const double *factor_host, int64_t nfactor,
+                    int64_t rows_per_factor, void *stream);
+int exb_inflate_f32(float *X, int64_t nrows, int nens, const double *factor_host, int64_t nfactor,
+                    int64_t rows_per_factor, void *stream);
+
+/* In place X[r][m] += xm[r]: the recombination in format_posterior_state
+ * (assimilation/assimilation.py:168). */
+int exb_recombine_f64(double *X, const double *xm, int64_t nrows, int nens, void *stream);
+int exb_recombine_f32(float *X, const float *xm, int64_t nrows, int nens, void *stream);
+
+/* ---- the serial loop, split in two (the obs rows are a closed subsystem) --- */
+/* Obs-space serial solve: the rows Nstate..Nstate+Nobs-1 of the reference's augmented state evolved
+ * through the whole loop ensrf.py:50-149 in the given (serial) order.
+ *   in : Ym[nobs], Yp[nobs][nens]  ob-prior means and perturbations (assimilation.py:149-150)
+ *   out: Yp[k][:] = ye_k, the ensemble of ob k as read when ob k is processed (ensrf.py:64);
+ *        Ym[k]    = mye_k (ensrf.py:63);  rec = per-ob records (see top).
+ * counters (device uint64[2], may be NULL): [0] += number of (ob k, obs row j >= k) pairs with
+ * non-zero localisation weight = sum_k |F_o(k)| of SURVEY.md section 8d. */
+int exb_obs_solve_f64(double *Ym, double *Yp, const double *ob_value, const double *ob_error,
+                      const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
+                      int loc_mode, double *rec, unsigned long long *counters, void *stream);
+int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, const double *ob_error,
+                      const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
+                      int loc_mode, double *rec, unsigned long long *counters, void *stream);
+
+/* State sweep over one latitude-band shard: applies obs [ob_begin, ob_end) in serial order to every
+ * state row of the shard -- kcov, localisation, gain, mean update and square-root perturbation update
+ * of ensrf.py:95-141 -- using the records of exb_obs_solve_*.
+ *   xm[nlev][ny*nx], Xp[nlev][ny*nx][nens]   the shard (ny = rows of this band), updated in place
+ *   grid_u double[3][ny*nx]                  unit vectors of the shard's grid points
+ *   Yp, rec, obgeo                           as written by exb_obs_solve_* / exb_obs_prepare
+ * counters (device uint64[2], may be NULL): [1] += number of (ob, grid point) pairs with non-zero
+ * weight = sum_k |F_s(k)| / nlev of SURVEY.md section 8d. */
+int exb_state_update_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                         const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
+                         int64_t nobs, int64_t ob_begin, int64_t ob_end, int loc_mode,
+                         unsigned long long *counters, void *stream);
+int exb_state_update_f32(float *xm, float *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                         const double *grid_u, const float *Yp, const double *rec, const double *obgeo,
+                         int64_t nobs, int64_t ob_begin, int64_t ob_end, int loc_mode,
+                         unsigned long long *counters, void *stream);
+
+/* ---- whole analysis with HOST buffers (one GPU) ------------------------------------------- */
+/* EnSRF(...).update() for callers that hold plain host arrays: uploads X, computes the ob priors,
+ * runs the serial analysis, downloads the analysis ensemble.  fp64 throughout.
+ *   X_host[nlev*ny*nx][nens]    in: prior ensemble; out: posterior ensemble (to_vect layout)
+ *   lat/lon_deg[ny*nx]          2-D grid coordinates, row-major (y, x)
+ *   ob_row0[nobs]               first state row of the ob's variable at its lower time level,
+ *                               ((var*nt + t_lo)*ny*nx); ob_row1 same for the upper time level
+ *   ob_tw0/ob_tw1[nobs]         time weights of those two levels (state/ensemble.py:202-224)
+ *   ob_diag[4][nobs]            out: prior_mean, prior_var, post_mean, post_var (ensrf.py:66-70,144-147)
+ *   inflation                   multiplicative factor applied first (1.0 = none)
+ *   stats[8]                    out, may be NULL: [0] sum|F_s| pairs, [1] sum|F_o| pairs, [2] n obs
+ *                               within 1 km of a grid point, [3..6] ms: upload, setup, analysis, download */
+int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                       const double *lat_deg, const double *lon_deg, int64_t nobs,
+                       const double *ob_value, const double *ob_error, const double *ob_lat_deg,
+                       const double *ob_lon_deg, const double *ob_halfwidth_km,
+                       const uint8_t *ob_assimilate, const int64_t *ob_row0, const int64_t *ob_row1,
+                       const double *ob_tw0, const double *ob_tw1, int loc_mode, double inflation,
+                       double *ob_diag, double *stats);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* Runs a dependent-free FP64 FMA loop on every SM and returns the achieved FMA rate in TFLOP/s
+ * (2 flop per FMA) through *tflops: the roofline denominator of the state sweep, which is bound by
+ * the FP64 pipe rather than by HBM. */
+int exb_measure_fp64_peak(double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFA_XRAY_B200_H */
