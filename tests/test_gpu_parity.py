@@ -78,8 +78,8 @@ def test_free_functions_match_reference_golden():
     from conftest import GOLDEN
     from efa_xray_b200.observation.observation import gaspari_cohn, haversine
     f = np.load(os.path.join(GOLDEN, 'functions.npz'))
-    np.testing.assert_allclose(gaspari_cohn(f['gc_d'], 1000.0), f['gc_w'], rtol=1e-13, atol=1e-16)
-    np.testing.assert_allclose(gaspari_cohn(f['gc_d'], -1000.0), f['gc_w_neg'], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(gaspari_cohn(f['gc_d'], 1000.0), f['gc_w'], rtol=1e-13, atol=1e-14)   # cancels to ~1e-15 near r=2
+    np.testing.assert_allclose(gaspari_cohn(f['gc_d'], -1000.0), f['gc_w_neg'], rtol=1e-13, atol=1e-14)
     hv = np.array([haversine((q[0], q[1]), (q[2], q[3])) for q in f['hv_pairs']])
     np.testing.assert_allclose(hv, f['hv_km'], rtol=1e-13, atol=1e-9)
 
