@@ -61,6 +61,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.argtypes = argtypes
         fn.restype = _int
+    lib.exb_launch_count.argtypes = []
+    lib.exb_launch_count.restype = C.c_int64
     lib.exb_last_error.argtypes = []
     lib.exb_last_error.restype = C.c_char_p
     _lib = lib
@@ -74,6 +76,11 @@ def call(name, *args):
     if rc != 0:
         raise ExbError('%s failed (%d): %s' % (name, rc, lib.exb_last_error().decode('utf-8', 'replace')))
     return rc
+
+
+def launch_count():
+    """Number of kernels this library has launched so far in this process."""
+    return int(load().exb_launch_count())
 
 
 def require_device():

@@ -25,6 +25,10 @@ int exb_check_launch(const char *what) {
     return EXB_OK;
 }
 
+static int64_t g_launches = 0;
+void exb_count_launches(int64_t n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
+extern "C" int64_t exb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" int exb_version(void) { return 100; }
 extern "C" const char *exb_last_error(void) { return g_err; }
 
@@ -72,6 +76,7 @@ extern "C" int exb_measure_fp64_peak(double *tflops, void *stream) {
     for (int rep = 0; rep < 4; ++rep) {
         EXB_CUDA(cudaEventRecord(e0, st));
         fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+        exb_count_launches(1);
         EXB_CUDA(cudaEventRecord(e1, st));
         EXB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -203,6 +208,7 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
                                                                      drow.as<int64_t>(), drow.as<int64_t>() + nobs,
                                                                      dtw.as<double>(), dtw.as<double>() + nobs, nobs,
                                                                      didx8.as<int64_t>(), dw8.as<double>());
+    exb_count_launches(1);
     EXB_TRY(exb_check_launch("stencil8_kernel"));
     EXB_TRY(exb_gather_f64(dX.as<double>(), nrows, nens, didx8.as<int64_t>(), dw8.as<double>(), 8, nobs,
                            dY.as<double>(), st));

@@ -29,6 +29,7 @@
 
 void exb_set_error(const char *fmt, ...);
 int exb_check_launch(const char *what);
+void exb_count_launches(int64_t n);   // bookkeeping for exb_launch_count()
 
 #define EXB_REQUIRE(cond, msg)                         \
     do {                                               \

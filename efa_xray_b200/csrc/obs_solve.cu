@@ -256,10 +256,12 @@ static int obs_solve_mc(T *Ym, T *Yp, const double *ob_value, const double *ob_e
     for (int64_t b0 = 0; b0 < nobs; b0 += PB) {
         obs_panel_kernel<T, MC><<<1, PB * GS, 0, st>>>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, b0,
                                                        loc_mode, rec, counters);
+        exb_count_launches(1);
         const int64_t rest = nobs - (b0 + PB);
         if (rest > 0) {
             const unsigned grid = (unsigned)ceil_div64(rest, TR_THREADS / GS);
             obs_trailing_kernel<T, MC><<<grid, TR_THREADS, 0, st>>>(Ym, Yp, geo, rec, nobs, nens, b0, loc_mode, counters);
+            exb_count_launches(1);
         }
     }
     return exb_check_launch("obs_solve kernels");

@@ -273,17 +273,20 @@ extern "C" int exb_localization_weights(const double *u, int64_t n, double ob_la
     }
     localization_weights_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
         u, n, cos(phi) * cos(lam), cos(phi) * sin(lam), sin(phi), inv_hw, a_max, loc_mode, dist, weights);
+    exb_count_launches(1);
     return exb_check_launch("localization_weights_kernel");
 }
 
 extern "C" int exb_gaspari_cohn(const double *d, int64_t n, double hw, double *w, void *stream) {
     EXB_REQUIRE(d && w && n > 0, "null pointer or n <= 0");
     gaspari_cohn_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(d, n, fabs(hw), w);
+    exb_count_launches(1);
     return exb_check_launch("gaspari_cohn_kernel");
 }
 extern "C" int exb_grid_unitvec(const double *lat, const double *lon, int64_t npts, double *grid_u, void *stream) {
     EXB_REQUIRE(lat && lon && grid_u && npts > 0, "null pointer or npts <= 0");
     grid_unitvec_kernel<<<(unsigned)ceil_div64(npts, 256), 256, 0, (cudaStream_t)stream>>>(lat, lon, npts, grid_u);
+    exb_count_launches(1);
     return exb_check_launch("grid_unitvec_kernel");
 }
 
@@ -292,6 +295,7 @@ extern "C" int exb_obs_prepare(const double *lat, const double *lon, const doubl
     EXB_REQUIRE(lat && lon && obgeo && nobs > 0, "null pointer or nobs <= 0");
     EXB_REQUIRE(loc_mode == EXB_LOC_NONE || (loc_mode == EXB_LOC_GC && hw), "loc_mode GC needs halfwidths");
     obs_prepare_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, (cudaStream_t)stream>>>(lat, lon, hw, nobs, loc_mode, obgeo);
+    exb_count_launches(1);
     return exb_check_launch("obs_prepare_kernel");
 }
 
@@ -311,6 +315,7 @@ extern "C" int exb_stencil_search(const double *sinlat_g, const double *coslon_g
     if (n_exact) EXB_CUDA(cudaMemsetAsync(n_exact, 0, sizeof(int32_t), (cudaStream_t)stream));
     nearest4_kernel<<<(unsigned)ceil_div64(nobs, NS_OBS_PER_CTA), NS_TX * NS_OY, smem, (cudaStream_t)stream>>>(
         sinlat_g, coslon_g, lat_g, lon_g, (int)npts, ob_sinlat, ob_coslon, ob_lat, ob_lon, nobs, idx4, w4, n_exact);
+    exb_count_launches(1);
     return exb_check_launch("nearest4_kernel");
 }
 
@@ -321,6 +326,7 @@ static int gather_impl(const T *X, int64_t nrows, int nens, const int64_t *idx, 
     EXB_REQUIRE(nrows > 0 && nens > 0 && nobs > 0 && K > 0 && K <= 8, "bad sizes (need 0 < K <= 8)");
     dim3 block(32, 8);
     gather_kernel<T><<<(unsigned)ceil_div64(nobs, 8), block, 0, (cudaStream_t)stream>>>(X, nens, idx, w, K, nobs, Y);
+    exb_count_launches(1);
     return exb_check_launch("gather_kernel");
 }
 extern "C" int exb_gather_f64(const double *X, int64_t nrows, int nens, const int64_t *idx, const double *w,
@@ -339,6 +345,7 @@ static int row_impl(T *X, T *xm, int64_t nrows, int nens, const double *factor_d
     const int64_t blocks = ceil_div64(nrows, 8);
     const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
     row_kernel<T, MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(X, xm, nrows, nens, factor_dev, rows_per_factor);
+    exb_count_launches(1);
     return exb_check_launch(what);
 }
 extern "C" int exb_split_mean_pert_f64(double *X, double *xm, int64_t nrows, int nens, void *stream) {

@@ -288,6 +288,7 @@ static int su_launch(SuParams &p, cudaStream_t st) {
     const int64_t nblocks = (int64_t)p.ntx * nty * p.nlc;
     EXB_REQUIRE(nblocks < 0x7fffffff, "too many patches for one launch");
     state_update_kernel<T, S, MC><<<(unsigned)nblocks, SU_NT, smem, st>>>(p);
+    exb_count_launches(1);
     return exb_check_launch("state_update_kernel");
 }
 
@@ -335,6 +336,7 @@ static int state_update_impl(T *xm, T *Xp, int64_t nlev, int64_t ny, int64_t nx,
     float4 *scan = nullptr;
     EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
+    exb_count_launches(1);
     SuParams p;
     p.xm = xm; p.Xp = Xp; p.Yp = Yp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
     p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;

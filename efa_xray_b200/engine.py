@@ -124,8 +124,11 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon):
     return idx4, w4, nex
 
 
-def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx):
-    """Y[nobs, nens] = H X for all obs (compute_ob_priors, assimilation/assimilation.py:36-49)."""
+def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, group=None):
+    """Y[nobs, nens] = H X for all obs (compute_ob_priors, assimilation/assimilation.py:36-49).
+
+    With band=(y0, y1), X holds only that latitude band of the state: each rank sums the stencil points it
+    owns and the partial sums are all-reduced, so every rank ends with the same full Y."""
     torch = _torch()
     dev = X.device
     idx4, w4, nex = stencil_search(grid, obs.lat, obs.lon)
@@ -133,11 +136,19 @@ def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx):
     row1 = torch.as_tensor(obs.row1).to(dev)
     tw0, tw1 = _dev_f64(obs.tw0, dev), _dev_f64(obs.tw1, dev)
     # 8-point stencil = 4 space points x 2 time levels (index/weight bookkeeping only)
-    idx8 = torch.cat([row0[:, None] + idx4, row1[:, None] + idx4], dim=1).contiguous()
-    w8 = torch.cat([tw0[:, None] * w4, tw1[:, None] * w4], dim=1).contiguous()
+    idx8 = torch.cat([row0[:, None] + idx4, row1[:, None] + idx4], dim=1)
+    w8 = torch.cat([tw0[:, None] * w4, tw1[:, None] * w4], dim=1)
+    if band is not None:
+        from .sharding import localize_stencil
+        idx8, w8 = localize_stencil(idx8, w8, nlev, grid.ny, grid.nx, band[0], band[1])
+    idx8, w8 = idx8.contiguous(), w8.contiguous()
     Y = torch.empty((obs.nobs, X.shape[1]), dtype=X.dtype, device=dev)
     _lib.call('exb_gather_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(idx8), _lib.ptr(w8), 8,
               obs.nobs, _lib.ptr(Y), _lib.stream_ptr())
+    if band is not None:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(Y, group=group)
     return Y, nex
 
 
@@ -200,20 +211,25 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
     return d, geo
 
 
-def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflation=None, timing=True):
+def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflation=None, timing=True,
+                    band=None, group=None, Y=None):
     """Serial EnSRF analysis of a device-resident ensemble, in place.
 
     X        torch tensor [nlev*ny*nx, nens] (float64 or float32) on a CUDA device, to_vect layout
-             (state/ensemble.py:110-114); overwritten with the analysis ensemble.
+             (state/ensemble.py:110-114); overwritten with the analysis ensemble.  With band=(y0, y1) X is
+             only that latitude band, [nlev*(y1-y0)*nx, nens], of a state sharded over the ranks of `group`;
+             `grid` always describes the full grid.
     inflation  None, or a numpy array of per-level multiplicative factors (length nlev).
-    Returns an AnalysisResult with the per-ob diagnostics of ensrf.py:66-70,144-149.
+    Returns an AnalysisResult with the per-ob diagnostics of ensrf.py:66-70,144-149 (identical on all ranks).
     """
     torch = _torch()
     _lib.require_device()
     sfx = _sfx(X.dtype)
     dev = X.device
     nrows, nens = X.shape
-    ny, nx = grid.ny, grid.nx
+    nx = grid.nx
+    y0, y1 = band if band is not None else (0, grid.ny)
+    ny = y1 - y0
     assert nrows == nlev * ny * nx, (nrows, nlev, ny, nx)
     assert X.is_contiguous()
     tm = _Timer(timing)
@@ -225,7 +241,10 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             _lib.call('exb_inflate_' + sfx, _lib.ptr(X), nrows, nens, fac.ctypes.data_as(C.c_void_p), nlev,
                       ny * nx, _lib.stream_ptr())
         obs_dev, geo = upload_obs(obs, dev, loc_mode)
-        Yp, nex = ob_priors(X, grid, obs, sfx)
+        if Y is None:
+            Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group)
+        else:       # ob priors H.x computed by the caller (e.g. before the state was scattered)
+            Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
         Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
         _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
         xm = torch.empty(nrows, dtype=X.dtype, device=dev)
@@ -235,7 +254,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         counters = torch.zeros(2, dtype=torch.int64, device=dev)
         obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx)
         tm.mark('obs_solve')
-        state_update(xm, X, nlev, ny, nx, grid.u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
+        grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
+        state_update(xm, X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
         tm.mark('state_update')
         _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
         tm.mark('recombine')
@@ -248,27 +268,29 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
 
 
 def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflation=None, device='cuda:0',
-                  dtype=None, grid=None):
+                  dtype=None, grid=None, out=None):
     """Host-buffer entry: X_host is a numpy array or CPU torch tensor [nlev*ny*nx, nens]; it is uploaded,
-    analysed on `device` and written back in place.  Pinned host memory makes the copies asynchronous."""
+    analysed on `device`, and the analysis is written to `out` (default: back into X_host).  Pinned host
+    memory makes the copies asynchronous.  res.ms gains 'upload' and 'download'."""
     torch = _torch()
     _lib.require_device()
     Xh = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(X_host)
-    assert Xh.is_contiguous()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ev2 = torch.cuda.Event(enable_timing=True)
+    Oh = Xh if out is None else (out if isinstance(out, torch.Tensor) else torch.from_numpy(out))
+    assert Xh.is_contiguous() and Oh.is_contiguous() and Oh.shape == Xh.shape
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     with torch.cuda.device(device):
-        ev0.record()
+        ev[0].record()
         X = Xh.to(device, non_blocking=True)
         if dtype is not None and X.dtype != dtype:
             X = X.to(dtype)
-        ev1.record()
+        ev[1].record()
         if grid is None:
             grid = GridTables(lat2d, lon2d, torch.device(device))
         res = analysis_device(X, nlev, grid, obs, loc_mode, inflation)
-        ev2.record()
-        Xh.copy_(X.to(Xh.dtype) if X.dtype != Xh.dtype else X)
+        ev[2].record()
+        Oh.copy_(X.to(Oh.dtype) if X.dtype != Oh.dtype else X, non_blocking=True)
+        ev[3].record()
         torch.cuda.synchronize()
-        res.ms['upload'] = ev0.elapsed_time(ev1)
+        res.ms['upload'] = ev[0].elapsed_time(ev[1])
+        res.ms['download'] = ev[2].elapsed_time(ev[3])
     return res

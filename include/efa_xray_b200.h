@@ -49,6 +49,7 @@ extern "C" {
 int exb_version(void);                       /* 100*major + minor                             */
 const char *exb_last_error(void);            /* message of the last failure on this thread    */
 int exb_device_check(void);                  /* 0 if the current device can run the kernels   */
+int64_t exb_launch_count(void);              /* kernels launched by this library so far        */
 
 /* ---- geometry --------------------------------------------------------------------------- */
 /* Unit vectors of grid points from lat/lon in degrees; out is SoA double[3][npts].
