@@ -38,6 +38,7 @@ SIGNATURES = {
     'exb_ensrf_host_f64': [_p, _i64, _i64, _i64, _int, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                            _int, _dbl, _p, _p],
     'exb_measure_fp64_peak': [_p, _p],
+    'exb_measure_dmma_peak': [_p, _p],
 }
 
 _lib = None

@@ -92,6 +92,53 @@ extern "C" int exb_measure_fp64_peak(double *tflops, void *stream) {
     return exb_check_launch("fp64_peak_kernel");
 }
 
+// FP64 tensor-core (DMMA, mma.sync m8n8k4) peak probe: 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = 0.5 * i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += c[i][0] + c[i][1];
+    if (r == 123.456) out[0] = r;
+}
+
+extern "C" int exb_measure_dmma_peak(double *tflops, void *stream) {
+    EXB_REQUIRE(tflops, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *out = nullptr;
+    EXB_CUDA(cudaMalloc(&out, sizeof(double)));
+    const int iters = 1 << 13, blocks = 148 * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    EXB_CUDA(cudaEventCreate(&e0));
+    EXB_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        EXB_CUDA(cudaEventRecord(e0, st));
+        dmma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 1e-3, 1e-3);
+        exb_count_launches(1);
+        EXB_CUDA(cudaEventRecord(e1, st));
+        EXB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        EXB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        // one m8n8k4 = 8*8*4 FMA = 512 flop per warp
+        const double flop = 512.0 * 8.0 * (double)iters * blocks * (threads / 32);
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return exb_check_launch("dmma_peak_kernel");
+}
+
 // ------------------------------------------------------------------------------------------
 // whole analysis with host buffers
 // ------------------------------------------------------------------------------------------

@@ -15,6 +15,14 @@
 // the lanes of a group) and stages the Q obs ensembles ye in shared memory, then each group applies the
 // Q obs in order to its row.
 #include "common.cuh"
+#include <type_traits>
+#include <cstring>
+#include <cstdlib>
+
+int exb_state_update_mma_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                             const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
+                             const float4 *scan, int64_t nobs, int64_t ob_begin, int64_t ob_end, int loc_mode,
+                             unsigned long long *counters, cudaStream_t st);
 
 #define SU_NT 256
 #define SU_QCAP 16
@@ -337,6 +345,18 @@ static int state_update_impl(T *xm, T *Xp, int64_t nlev, int64_t ny, int64_t nx,
     EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
     exb_count_launches(1);
+    if (std::is_same<T, double>::value) {
+        // float64 states: blocked FP64 tensor-core sweep (state_update_mma.cu) unless EXB_SU_IMPL=vector
+        const char *impl = getenv("EXB_SU_IMPL");
+        if (!(impl && strcmp(impl, "vector") == 0)) {
+            int rc = exb_state_update_mma_f64((double *)xm, (double *)Xp, nlev, ny, nx, nens, grid_u, (const double *)Yp,
+                                              rec, obgeo, scan, nobs, ob_begin, ob_end, loc_mode, counters, st);
+            if (rc != EXB_ERR_UNSUPPORTED) {
+                cudaFreeAsync(scan, st);
+                return rc;
+            }
+        }
+    }
     SuParams p;
     p.xm = xm; p.Xp = Xp; p.Yp = Yp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
     p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;

@@ -173,6 +173,9 @@ int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int64_t nx, int
  * the FP64 pipe rather than by HBM. */
 int exb_measure_fp64_peak(double *tflops, void *stream);
 
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4 f64, SASS DMMA) used by the blocked state sweep. */
+int exb_measure_dmma_peak(double *tflops, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
