@@ -21,6 +21,7 @@ SIGNATURES = {
     'exb_grid_unitvec': [_p, _p, _i64, _p, _p],
     'exb_obs_prepare': [_p, _p, _p, _i64, _int, _p, _p],
     'exb_stencil_search': [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
+    'exb_stencil_search_rect': [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     'exb_gather_f64': [_p, _i64, _int, _p, _p, _int, _i64, _p, _p],
     'exb_gather_f32': [_p, _i64, _int, _p, _p, _int, _i64, _p, _p],
     'exb_split_mean_pert_f64': [_p, _p, _i64, _int, _p],

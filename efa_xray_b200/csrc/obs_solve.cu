@@ -44,8 +44,13 @@ obs_panel_kernel(T *__restrict__ Ym, T *__restrict__ Yp, const double *__restric
                  const double *__restrict__ ob_error, const uint8_t *__restrict__ ob_assim,
                  const double *__restrict__ geo, int64_t nobs, int nens, int64_t b0, int loc_mode,
                  double *__restrict__ rec, unsigned long long *__restrict__ counters) {
-    __shared__ T s_ye[GS * MC];
-    __shared__ ObScalars s_ob;
+    // Serial chain, one step per ob.  Everything that does not depend on the evolving rows is taken out of
+    // the loop: the PB x PB pairwise localisation weights are evaluated in parallel first, and the broadcast
+    // buffers are double-buffered so that a step needs one barrier.
+    __shared__ T s_ye[2][GS * MC];
+    __shared__ ObScalars s_ob[2];
+    __shared__ double s_W[PB * PB];          // s_W[k*PB + j]: weight of ob k at row j (j > k)
+    __shared__ double s_g[5][PB];
 
     const int g = threadIdx.x / GS;          // row within the panel
     const int s = threadIdx.x % GS;
@@ -62,58 +67,80 @@ obs_panel_kernel(T *__restrict__ Ym, T *__restrict__ Yp, const double *__restric
         x[i] = (valid && m < nens) ? Yp[j * nens + m] : (T)0;
     }
     double mj = valid ? (double)Ym[j] : 0.0;
-    double ux = 0, uy = 0, uz = 0;
-    if (valid) { ux = geo[GEO_UX * nobs + j]; uy = geo[GEO_UY * nobs + j]; uz = geo[GEO_UZ * nobs + j]; }
+    for (int i = threadIdx.x; i < PB; i += PB * GS) {
+        const int64_t kk = (b0 + i < nobs) ? b0 + i : nobs - 1;
+        s_g[0][i] = geo[GEO_UX * nobs + kk];
+        s_g[1][i] = geo[GEO_UY * nobs + kk];
+        s_g[2][i] = geo[GEO_UZ * nobs + kk];
+        s_g[3][i] = geo[GEO_INVHW * nobs + kk];
+        s_g[4][i] = geo[GEO_AMAX * nobs + kk];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PB * PB; idx += PB * GS) {
+        const int k = idx / PB, jj = idx % PB;
+        double w = 0.0;
+        if (jj > k && jj < nb) {
+            w = 1.0;
+            if (loc_mode == EXB_LOC_GC)
+                w = loc_weight(hav_a(s_g[0][jj], s_g[1][jj], s_g[2][jj], s_g[0][k], s_g[1][k], s_g[2][k]),
+                               s_g[3][k], s_g[4][k]);
+        }
+        s_W[idx] = w;
+    }
+    // per-ob inputs of this row when it becomes the active ob (only lane s == 0 of the group uses them)
+    double my_val = 0.0, my_err = 1.0, my_wself = 1.0;
+    int my_assim = 0;
+    if (valid && s == 0) {
+        my_val = ob_value[j];
+        my_err = ob_error[j];
+        my_assim = ob_assim[j] != 0;
+        my_wself = (loc_mode == EXB_LOC_GC) ? loc_weight(0.0, s_g[3][g], s_g[4][g]) : 1.0;
+    }
     unsigned long long npairs = 0;
+    __syncthreads();
 
     for (int k = 0; k < nb; ++k) {
+        const int buf = k & 1;
         if (g == k) {
-            // ensrf.py:63-70: mye, ye, varye = np.var(ye) (ddof 0)
-            double sum = 0.0;
+            // ensrf.py:63-70: mye, ye, varye = np.var(ye) (ddof 0), here as E[x^2] - mean^2
+            double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < MC; ++i) sum += (double)x[i];
-            sum = group_sum<GS>(sum, gmask);
-            const double mean = sum / (double)nens;
-            double ss = 0.0, sq = 0.0;
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (s + GS * i < nens) {
-                    const double d = (double)x[i] - mean;
-                    ss += d * d;
-                    sq += (double)x[i] * (double)x[i];
-                }
+            for (int i = 0; i < MC; i += 2) {
+                const double a = (double)x[i];
+                s0 += a; q0 += a * a;
+                if (i + 1 < MC) { const double b = (double)x[i + 1]; s1 += b; q1 += b * b; }
             }
-            ss = group_sum<GS>(ss, gmask);
-            sq = group_sum<GS>(sq, gmask);
-            const double varye = ss / (double)nens;
+            double sum = s0 + s1, sq = q0 + q1;
 #pragma unroll
-            for (int i = 0; i < MC; ++i) s_ye[s * MC + i] = x[i];
+            for (int off = GS / 2; off > 0; off >>= 1) {
+                sum += __shfl_xor_sync(gmask, sum, off);
+                sq += __shfl_xor_sync(gmask, sq, off);
+            }
+#pragma unroll
+            for (int i = 0; i < MC; ++i) s_ye[buf][s * MC + i] = x[i];
             if (s == 0) {
                 const int64_t kk = b0 + k;
-                const int assim = ob_assim[kk] != 0;
-                const double err = ob_error[kk];
-                const double inv_hw = geo[GEO_INVHW * nobs + kk], a_max = geo[GEO_AMAX * nobs + kk];
-                const double innov = ob_value[kk] - mj;                    // ensrf.py:86
-                const double kdenom = varye + err;                          // ensrf.py:91
-                const double c1 = 1.0 / ((double)(nens - 1) * kdenom);      // ensrf.py:95, :119
-                const double beta = 1.0 / (1.0 + sqrt(err / kdenom));       // ensrf.py:135
-                s_ob.ux = ux; s_ob.uy = uy; s_ob.uz = uz;
-                s_ob.inv_hw = inv_hw; s_ob.a_max = a_max;
-                s_ob.innov = innov; s_ob.c1 = c1; s_ob.beta = beta; s_ob.assim = assim;
-                rec[REC_PRIOR_MEAN * nobs + kk] = mj;                       // ensrf.py:66
-                rec[REC_PRIOR_VAR * nobs + kk] = varye;                     // ensrf.py:70
+                const double inv_n = 1.0 / (double)nens;
+                const double mean = sum * inv_n;
+                const double varye = fmax(sq * inv_n - mean * mean, 0.0);
+                const double innov = my_val - mj;                            // ensrf.py:86
+                const double kdenom = varye + my_err;                         // ensrf.py:91
+                const double c1 = 1.0 / ((double)(nens - 1) * kdenom);        // ensrf.py:95, :119
+                const double beta = 1.0 / (1.0 + sqrt(my_err / kdenom));      // ensrf.py:135
+                s_ob[buf].innov = innov; s_ob[buf].c1 = c1; s_ob[buf].beta = beta; s_ob[buf].assim = my_assim;
+                rec[REC_PRIOR_MEAN * nobs + kk] = mj;                         // ensrf.py:66
+                rec[REC_PRIOR_VAR * nobs + kk] = varye;                       // ensrf.py:70
                 rec[REC_INNOV * nobs + kk] = innov;
                 rec[REC_C1 * nobs + kk] = c1;
                 rec[REC_BETA * nobs + kk] = beta;
-                rec[REC_ASSIM * nobs + kk] = assim ? 1.0 : 0.0;
-                if (assim) {
+                rec[REC_ASSIM * nobs + kk] = my_assim ? 1.0 : 0.0;
+                if (my_assim) {
                     // the ob's own row: weight at distance 0, kcov = ye.ye/(N-1)  (ensrf.py:144-147)
-                    const double wself = (loc_mode == EXB_LOC_GC) ? loc_weight(0.0, inv_hw, a_max) : 1.0;
-                    const double kmat = wself * sq * c1;
+                    const double kmat = my_wself * sq * c1;
                     const double shrink = 1.0 - beta * kmat;
                     rec[REC_POST_MEAN * nobs + kk] = mj + kmat * innov;
                     rec[REC_POST_VAR * nobs + kk] = varye * shrink * shrink;
-                    if (wself != 0.0) npairs++;
+                    if (my_wself != 0.0) npairs++;
                 } else {
                     rec[REC_POST_MEAN * nobs + kk] = nan("");
                     rec[REC_POST_VAR * nobs + kk] = nan("");
@@ -121,28 +148,29 @@ obs_panel_kernel(T *__restrict__ Ym, T *__restrict__ Yp, const double *__restric
             }
         }
         __syncthreads();
-        if (s_ob.assim && g > k && valid) {
-            double w = 1.0;
-            if (loc_mode == EXB_LOC_GC)
-                w = loc_weight(hav_a(ux, uy, uz, s_ob.ux, s_ob.uy, s_ob.uz), s_ob.inv_hw, s_ob.a_max);
+        if (g > k && valid && s_ob[buf].assim) {
+            const double w = s_W[k * PB + g];
             if (w != 0.0) {
                 T ye[MC];
-                double dot = 0.0;
+                T d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
-                for (int i = 0; i < MC; ++i) {
-                    ye[i] = s_ye[s * MC + i];
-                    dot += (double)(x[i] * ye[i]);
+                for (int i = 0; i < MC; ++i) ye[i] = s_ye[buf][s * MC + i];
+#pragma unroll
+                for (int i = 0; i < MC; i += 4) {
+                    d0 += x[i] * ye[i];
+                    if (i + 1 < MC) d1 += x[i + 1] * ye[i + 1];
+                    if (i + 2 < MC) d2 += x[i + 2] * ye[i + 2];
+                    if (i + 3 < MC) d3 += x[i + 3] * ye[i + 3];
                 }
-                dot = group_sum<GS>(dot, gmask);
-                const double kmat = w * dot * s_ob.c1;              // loc * kcov / kdenom, ensrf.py:115-119
-                mj += kmat * s_ob.innov;                            // ensrf.py:130
-                const T f = (T)(s_ob.beta * kmat);                  // ensrf.py:136
+                const double dot = group_sum<GS>((double)((d0 + d1) + (d2 + d3)), gmask);
+                const double kmat = w * dot * s_ob[buf].c1;         // loc * kcov / kdenom, ensrf.py:115-119
+                mj += kmat * s_ob[buf].innov;                       // ensrf.py:130
+                const T f = (T)(s_ob[buf].beta * kmat);             // ensrf.py:136
 #pragma unroll
                 for (int i = 0; i < MC; ++i) x[i] -= f * ye[i];     // ensrf.py:141
                 if (s == 0) npairs++;
             }
         }
-        __syncthreads();
     }
     if (valid) {
 #pragma unroll

@@ -188,6 +188,123 @@ nearest4_kernel(const double *__restrict__ sl_g, const double *__restrict__ cl_g
     }
 }
 
+// Rectilinear grids (lat depends on y only, lon on x only -- every regular lat-lon grid): the squared
+// pseudo-distance separates, d2(y, x) = A[y] + B[x] with A = (sin lat_y - sin lat_ob)^2 and
+// B = (cos lon_x - cos lon_ob)^2, so the 4 smallest d2 are among the 8 smallest A x the 8 smallest B.
+// Same roundings and the same (d2, flat index) order as nearest4_kernel, at O(ny + nx) per ob.
+#define NR_K 8
+#define NR_WARPS 8
+
+template <int K>
+__device__ __forceinline__ void topk_insert(double (&d)[K], int (&ix)[K], double v, int p) {
+    if (!(v < d[K - 1])) return;
+    bool placed = false;
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+        if (!placed) {
+            if (v < d[j - 1]) { d[j] = d[j - 1]; ix[j] = ix[j - 1]; }
+            else { d[j] = v; ix[j] = p; placed = true; }
+        }
+    }
+    if (!placed) { d[0] = v; ix[0] = p; }
+}
+
+// the warp picks the `nsel` smallest (d, i) keys among ncand candidates in shared memory, in order
+__device__ __forceinline__ void warp_select(const double *cd, const int *ci, int ncand, int nsel, int lane,
+                                            double *out_d, int *out_i) {
+    double prev_d = -1.0;
+    int prev_i = -1;
+    for (int r = 0; r < nsel; ++r) {
+        double md = INFINITY;
+        int mi = 0x7fffffff;
+        for (int c = lane; c < ncand; c += 32) {
+            const double d = cd[c];
+            const int i = ci[c];
+            if (key_less(prev_d, prev_i, d, i) && key_less(d, i, md, mi)) { md = d; mi = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, md, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+            if (key_less(od, oi, md, mi)) { md = od; mi = oi; }
+        }
+        if (lane == 0) { out_d[r] = md; out_i[r] = mi; }
+        prev_d = md;
+        prev_i = mi;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * NR_WARPS)
+nearest4_rect_kernel(const double *__restrict__ sl_y, const double *__restrict__ cl_x,
+                     const double *__restrict__ lat_y, const double *__restrict__ lon_x, int ny, int nx,
+                     const double *__restrict__ ob_sl, const double *__restrict__ ob_cl,
+                     const double *__restrict__ ob_lat, const double *__restrict__ ob_lon, int64_t nobs,
+                     int64_t *__restrict__ idx4, double *__restrict__ w4, int32_t *__restrict__ n_exact) {
+    __shared__ double s_d[NR_WARPS][32 * NR_K];
+    __shared__ int s_i[NR_WARPS][32 * NR_K];
+    __shared__ double s_ad[NR_WARPS][NR_K], s_bd[NR_WARPS][NR_K], s_fd[NR_WARPS][4];
+    __shared__ int s_ai[NR_WARPS][NR_K], s_bi[NR_WARPS][NR_K], s_fi[NR_WARPS][4];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t k = blockIdx.x * (int64_t)NR_WARPS + warp;
+    if (k >= nobs) return;
+    const double osl = ob_sl[k], ocl = ob_cl[k];
+    double d[NR_K];
+    int ix[NR_K];
+    // 8 smallest A[y] (ties: lowest y)
+#pragma unroll
+    for (int j = 0; j < NR_K; ++j) { d[j] = INFINITY; ix[j] = 0x7fffffff; }
+    for (int y = lane; y < ny; y += 32) {
+        const double a = sl_y[y] - osl;
+        topk_insert<NR_K>(d, ix, __dmul_rn(a, a), y);
+    }
+#pragma unroll
+    for (int j = 0; j < NR_K; ++j) { s_d[warp][lane * NR_K + j] = d[j]; s_i[warp][lane * NR_K + j] = ix[j]; }
+    __syncwarp();
+    warp_select(s_d[warp], s_i[warp], 32 * NR_K, NR_K, lane, s_ad[warp], s_ai[warp]);
+    // 8 smallest B[x] (ties: lowest x)
+#pragma unroll
+    for (int j = 0; j < NR_K; ++j) { d[j] = INFINITY; ix[j] = 0x7fffffff; }
+    for (int x = lane; x < nx; x += 32) {
+        const double b = cl_x[x] - ocl;
+        topk_insert<NR_K>(d, ix, __dmul_rn(b, b), x);
+    }
+#pragma unroll
+    for (int j = 0; j < NR_K; ++j) { s_d[warp][lane * NR_K + j] = d[j]; s_i[warp][lane * NR_K + j] = ix[j]; }
+    __syncwarp();
+    warp_select(s_d[warp], s_i[warp], 32 * NR_K, NR_K, lane, s_bd[warp], s_bi[warp]);
+    // 64 combinations -> 4 smallest by (d2, flat index)
+    for (int cidx = lane; cidx < NR_K * NR_K; cidx += 32) {
+        const int i = cidx / NR_K, j = cidx % NR_K;
+        const int yy = s_ai[warp][i], xx = s_bi[warp][j];
+        const bool ok = yy < ny && xx < nx;
+        s_d[warp][cidx] = ok ? __dadd_rn(s_ad[warp][i], s_bd[warp][j]) : INFINITY;
+        s_i[warp][cidx] = ok ? yy * nx + xx : 0x7fffffff;
+    }
+    __syncwarp();
+    warp_select(s_d[warp], s_i[warp], NR_K * NR_K, 4, lane, s_fd[warp], s_fi[warp]);
+    if (lane == 0) {
+        double dist[4], w[4];
+        int amin = 0;
+        bool exact = false;
+        for (int r = 0; r < 4; ++r) {
+            const int f = s_fi[warp][r];
+            dist[r] = haversine_ref(lat_y[f / nx], lon_x[f % nx], ob_lat[k], ob_lon[k]);
+            if (dist[r] < 1.0) exact = true;
+            if (dist[r] < dist[amin]) amin = r;
+        }
+        if (exact) {
+            for (int r = 0; r < 4; ++r) w[r] = (r == amin) ? 1.0 : 0.0;
+            if (n_exact) atomicAdd(n_exact, 1);
+        } else {
+            double s = 0.0;
+            for (int r = 0; r < 4; ++r) { w[r] = 1.0 / dist[r]; s += w[r]; }
+            for (int r = 0; r < 4; ++r) w[r] /= s;
+        }
+        for (int r = 0; r < 4; ++r) { idx4[k * 4 + r] = s_fi[warp][r]; w4[k * 4 + r] = w[r]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K-point weighted gather: Y[k][m] = sum_p w[k][p] X[idx[k][p]][m]   (state/ensemble.py:226-237)
 // ------------------------------------------------------------------------------------------
@@ -317,6 +434,22 @@ extern "C" int exb_stencil_search(const double *sinlat_g, const double *coslon_g
         sinlat_g, coslon_g, lat_g, lon_g, (int)npts, ob_sinlat, ob_coslon, ob_lat, ob_lon, nobs, idx4, w4, n_exact);
     exb_count_launches(1);
     return exb_check_launch("nearest4_kernel");
+}
+
+extern "C" int exb_stencil_search_rect(const double *sinlat_y, const double *coslon_x, const double *lat_y,
+                                       const double *lon_x, int64_t ny, int64_t nx, const double *ob_sinlat,
+                                       const double *ob_coslon, const double *ob_lat, const double *ob_lon,
+                                       int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream) {
+    EXB_REQUIRE(sinlat_y && coslon_x && lat_y && lon_x && ob_sinlat && ob_coslon && ob_lat && ob_lon && idx4 && w4,
+                "null pointer");
+    EXB_REQUIRE(ny > 0 && nx > 0 && ny * nx >= 4 && ny * nx < 0x7fffffff && nobs > 0,
+                "need 4 <= ny*nx < 2^31 and nobs > 0");
+    if (n_exact) EXB_CUDA(cudaMemsetAsync(n_exact, 0, sizeof(int32_t), (cudaStream_t)stream));
+    nearest4_rect_kernel<<<(unsigned)ceil_div64(nobs, NR_WARPS), 32 * NR_WARPS, 0, (cudaStream_t)stream>>>(
+        sinlat_y, coslon_x, lat_y, lon_x, (int)ny, (int)nx, ob_sinlat, ob_coslon, ob_lat, ob_lon, nobs, idx4, w4,
+        n_exact);
+    exb_count_launches(1);
+    return exb_check_launch("nearest4_rect_kernel");
 }
 
 template <typename T>

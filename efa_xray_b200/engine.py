@@ -99,12 +99,19 @@ class GridTables:
         self.lon = _dev_f64(lon2d.ravel(), device)
         self.sinlat = _dev_f64(np.sin(np.radians(lat2d)).ravel(), device)
         self.coslon = _dev_f64(np.cos(np.radians(lon2d)).ravel(), device)
+        # rectilinear grid (lat = f(y), lon = f(x)): the nearest-point search separates (O(ny+nx) per ob)
+        self.rectilinear = bool((lat2d == lat2d[:, :1]).all() and (lon2d == lon2d[:1, :]).all())
+        if self.rectilinear:
+            self.lat_y = _dev_f64(lat2d[:, 0], device)
+            self.lon_x = _dev_f64(lon2d[0, :], device)
+            self.sinlat_y = _dev_f64(np.sin(np.radians(lat2d[:, 0])), device)
+            self.coslon_x = _dev_f64(np.cos(np.radians(lon2d[0, :])), device)
         self.u = torch.empty((3, self.npts), dtype=torch.float64, device=device)
         _lib.call('exb_grid_unitvec', _lib.ptr(self.lat), _lib.ptr(self.lon), self.npts, _lib.ptr(self.u),
                   _lib.stream_ptr())
 
 
-def stencil_search(grid: GridTables, ob_lat, ob_lon):
+def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False):
     """4 nearest points (pseudo-metric) and inverse-distance weights for every ob -> device tensors
     idx4 [nobs,4] int64, w4 [nobs,4] float64, and the number of obs within 1 km of a selected point."""
     torch = _torch()
@@ -118,9 +125,14 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon):
     idx4 = torch.empty((nobs, 4), dtype=torch.int64, device=dev)
     w4 = torch.empty((nobs, 4), dtype=torch.float64, device=dev)
     nex = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.call('exb_stencil_search', _lib.ptr(grid.sinlat), _lib.ptr(grid.coslon), _lib.ptr(grid.lat),
-              _lib.ptr(grid.lon), grid.npts, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat), _lib.ptr(d_lon),
-              nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
+    if grid.rectilinear and not force_general:
+        _lib.call('exb_stencil_search_rect', _lib.ptr(grid.sinlat_y), _lib.ptr(grid.coslon_x), _lib.ptr(grid.lat_y),
+                  _lib.ptr(grid.lon_x), grid.ny, grid.nx, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat),
+                  _lib.ptr(d_lon), nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
+    else:
+        _lib.call('exb_stencil_search', _lib.ptr(grid.sinlat), _lib.ptr(grid.coslon), _lib.ptr(grid.lat),
+                  _lib.ptr(grid.lon), grid.npts, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat), _lib.ptr(d_lon),
+                  nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
     return idx4, w4, nex
 
 

@@ -88,6 +88,15 @@ int exb_stencil_search(const double *sinlat_g, const double *coslon_g, const dou
                        const double *ob_coslon, const double *ob_lat_deg, const double *ob_lon_deg,
                        int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream);
 
+/* Same search for RECTILINEAR grids (lat a function of y only, lon of x only -- every regular lat-lon
+ * grid): the squared pseudo-distance separates into A[y] + B[x], so the search costs O(ny + nx) per ob
+ * instead of O(ny * nx).  Tables are per row / per column; results are bit-identical to
+ * exb_stencil_search on the expanded 2-D tables. */
+int exb_stencil_search_rect(const double *sinlat_y, const double *coslon_x, const double *lat_y_deg,
+                            const double *lon_x_deg, int64_t ny, int64_t nx, const double *ob_sinlat,
+                            const double *ob_coslon, const double *ob_lat_deg, const double *ob_lon_deg,
+                            int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream);
+
 /* Y[k][m] = sum_p w[k][p] * X[idx[k][p]][m], p < K (K <= 8): the gather + weighted sums of
  * interpolate (state/ensemble.py:226-237) for all obs at once (compute_ob_priors,
  * assimilation/assimilation.py:36-49).  idx are ROW indices into X. */

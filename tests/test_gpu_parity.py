@@ -218,3 +218,27 @@ def test_host_buffer_c_abi_entry():
     np.testing.assert_allclose(diag[0], g['prior_mean'], rtol=1e-9)
     np.testing.assert_allclose(diag[3], g['post_var'], rtol=1e-9, equal_nan=True)
     assert stats[0] > 0 and stats[1] > 0 and stats[2] == 0
+
+
+def test_rectilinear_search_is_bit_identical_to_brute_force():
+    """The separable O(ny+nx) nearest-4 search against the brute-force kernel: same indices in the same
+    order and the same weights, including obs next to the 0/180 meridians, the poles and the equator."""
+    import torch
+    from efa_xray_b200 import engine
+    from efa_xray_b200.synth import regular_grid
+    rng = np.random.default_rng(5)
+    for ny, nx in ((19, 36), (46, 90), (181, 360), (5, 7)):
+        lat2d, lon2d = regular_grid(ny, nx)
+        grid = engine.GridTables(lat2d, lon2d, torch.device('cuda', 0))
+        assert grid.rectilinear
+        n = 600
+        lat = np.concatenate([np.degrees(np.arcsin(rng.uniform(-1, 1, n))), rng.uniform(-1, 1, 40), rng.uniform(86, 90, 20),
+                              rng.uniform(-90, -86, 20)])
+        lon = np.concatenate([rng.uniform(0, 360, n), rng.uniform(0, 360, 40), rng.uniform(0, 360, 40)])
+        lon[:60] = rng.uniform(-3, 3, 60) % 360
+        lon[60:120] = 180 + rng.uniform(-3, 3, 60)
+        i_r, w_r, n_r = engine.stencil_search(grid, lat, lon)
+        i_g, w_g, n_g = engine.stencil_search(grid, lat, lon, force_general=True)
+        assert torch.equal(i_r, i_g)
+        assert torch.equal(w_r, w_g)
+        assert int(n_r.item()) == int(n_g.item())
