@@ -16,9 +16,9 @@
 //   memory now feeds 8 FMAs instead of 2; the one-ob-at-a-time kernel was bound by the shared-memory pipe
 //   (profiles/r01_state_update_v1.md), not by FP64.
 //
-// The ensemble mean of a row is carried as a pseudo-member: column `nens` of the row holds xm, and the
-// staged y_q holds -innov_q/beta_q there, so the rank-8 update also performs xam = xbm + kmat*innov
-// (ensrf.py:130).  That column is masked out of the dot products.
+// The ensemble mean of a row is carried as a pseudo-member: the LAST padded column (8*NT3-1) of the row
+// holds xm, and the staged y_q holds -innov_q/beta_q there, so the rank-8 update also performs
+// xam = xbm + kmat*innov (ensrf.py:130).  That column is masked out of the dot products.
 //
 // Fragment layout (m8n8k4, f64): A[8x4] lane l -> A[l/4][l%4]; B[4x8] lane l -> B[l%4][l/4];
 // C[8x8] lane l -> C[l/4][2(l%4)], C[l/4][2(l%4)+1].  A warp owns 8 state rows (row = l/4); lane c = l%4 of a
@@ -61,12 +61,15 @@ __global__ void __launch_bounds__(SM_NT, MINB)
 state_update_mma_kernel(const SmParams p) {
     constexpr int YST = sm_yst<NT3>();
 
+    constexpr int PC = 8 * NT3 - 1;          // column of the pseudo-member (the mean)
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_y = reinterpret_cast<double *>(smem_raw);                 // [SM_Q][YST]
     double *s_om = s_y + SM_Q * YST;                                    // [SM_ROWS grid slots][SM_Q]
     double *s_G = s_om + SM_ROWS * SM_Q;                                // [SM_Q/8][8][8]
     double *s_gu = s_G + (SM_Q / 8) * 64;                               // [3][SM_ROWS]
-    int *s_cand = reinterpret_cast<int *>(s_gu + 3 * SM_ROWS);          // [SM_Q + SM_NT] queue of ob indices
+    double *s_ob = s_gu + 3 * SM_ROWS;                                  // [6][SM_Q] ux uy uz inv_hw a_max c1*beta
+    int *s_cand = reinterpret_cast<int *>(s_ob + 6 * SM_Q);             // [SM_Q + SM_NT] queue of ob indices
     int *s_gvalid = s_cand + SM_Q + SM_NT;                              // [SM_ROWS]
     int *s_warp = s_gvalid + SM_ROWS;                                   // [SM_NT/32]
     __shared__ float s_bound[4];
@@ -125,13 +128,12 @@ state_update_mma_kernel(const SmParams p) {
             double v = 0.0;
             if (active) {
                 if (m < nens) v = p.Xp[row * nens + m];
-                else if (m == nens) v = p.xm[row];          // the mean rides along as pseudo-member `nens`
+                else if (m == PC) v = p.xm[row];            // the mean rides along in the last column
             }
             x[2 * t + h] = v;
         }
     }
-    // which of this lane's registers is the pseudo-member (masked out of dot products)
-    const int jstar = (((nens >> 1) & 3) == c) ? 2 * (nens >> 3) + (nens & 1) : -1;
+    const float inv_G = 1.0f / (float)G;
     unsigned long long npairs = 0;
     bool dirty = false;
     __syncthreads();
@@ -170,35 +172,63 @@ state_update_mma_kernel(const SmParams p) {
         if (nq == 0) break;
         const int nb = (nq + 7) >> 3;
 
-        // ---- stage the round: omega[g][q], y_q (swizzled), zero padding of the last batch -----------
+        // ---- stage the round ------------------------------------------------------------------------
+        // (a) per-candidate scalars, (b) y_q rows by cp.async (one warp per row, swizzled columns)
+        if (tid < nb * 8) {
+            double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+            if (tid < nq) {
+                const int64_t kk = p.ob_begin + s_cand[tid];
+                v0 = p.geo[GEO_UX * p.nobs + kk]; v1 = p.geo[GEO_UY * p.nobs + kk]; v2 = p.geo[GEO_UZ * p.nobs + kk];
+                v3 = p.geo[GEO_INVHW * p.nobs + kk]; v4 = p.geo[GEO_AMAX * p.nobs + kk];
+                // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it below
+                v5 = p.rec[REC_C1 * p.nobs + kk] * p.rec[REC_BETA * p.nobs + kk];
+            }
+            s_ob[0 * SM_Q + tid] = v0; s_ob[1 * SM_Q + tid] = v1; s_ob[2 * SM_Q + tid] = v2;
+            s_ob[3 * SM_Q + tid] = v3; s_ob[4 * SM_Q + tid] = v4; s_ob[5 * SM_Q + tid] = v5;
+        }
+        for (int q = warp; q < nb * 8; q += SM_NT / 32) {
+            double *dst = s_y + q * YST;
+            const int sw = ((q >> 1) & 1) << 2;
+            if (q < nq) {
+                const int64_t kk = p.ob_begin + s_cand[q];
+                const double *src = p.Yp + kk * nens;
+                if ((nens & 1) == 0) {
+                    for (int m = 2 * lane; m < nens; m += 64) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (m ^ sw));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(src + m));
+                    }
+                } else {
+                    for (int m = lane; m < nens; m += 32) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (m ^ sw));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(src + m));
+                    }
+                }
+                if (lane == 0)
+                    dst[PC ^ sw] = -p.rec[REC_INNOV * p.nobs + kk] / p.rec[REC_BETA * p.nobs + kk];
+            } else {
+                for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
+                if (lane == 0) dst[PC ^ sw] = 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        __syncthreads();
+        // (c) omega[g][q] = beta * loc / ((N-1) kdenom), one (ob, grid point) pair at a time per thread
         for (int i = tid; i < nb * 8 * G; i += SM_NT) {
-            const int q = i / G, gg = i % G;
+            const int q = (int)(((float)i + 0.5f) * inv_G), gg = i - q * G;
             double om = 0.0;
             if (q < nq && s_gvalid[gg]) {
-                const int64_t kk = p.ob_begin + s_cand[q];
                 double w = 1.0;
                 if (p.loc_mode == EXB_LOC_GC) {
                     const double a = hav_a(s_gu[gg], s_gu[SM_ROWS + gg], s_gu[2 * SM_ROWS + gg],
-                                           p.geo[GEO_UX * p.nobs + kk], p.geo[GEO_UY * p.nobs + kk],
-                                           p.geo[GEO_UZ * p.nobs + kk]);
-                    w = loc_weight(a, p.geo[GEO_INVHW * p.nobs + kk], p.geo[GEO_AMAX * p.nobs + kk]);
+                                           s_ob[0 * SM_Q + q], s_ob[1 * SM_Q + q], s_ob[2 * SM_Q + q]);
+                    w = loc_weight(a, s_ob[3 * SM_Q + q], s_ob[4 * SM_Q + q]);
                 }
                 if (w != 0.0 && lc == 0) npairs++;
-                // beta * loc * 1/((N-1) kdenom)   (ensrf.py:95, :115-119, :135-136)
-                om = w * p.rec[REC_C1 * p.nobs + kk] * p.rec[REC_BETA * p.nobs + kk];
+                om = w * s_ob[5 * SM_Q + q];
             }
             s_om[gg * SM_Q + q] = om;
         }
-        for (int e = tid; e < nb * 8 * (nens + 1); e += SM_NT) {
-            const int q = e / (nens + 1), m = e % (nens + 1);
-            double v = 0.0;
-            if (q < nq) {
-                const int64_t kk = p.ob_begin + s_cand[q];
-                v = (m < nens) ? p.Yp[kk * nens + m]
-                               : -p.rec[REC_INNOV * p.nobs + kk] / p.rec[REC_BETA * p.nobs + kk];
-            }
-            s_y[q * YST + sm_swz(q, m)] = v;
-        }
+        asm volatile("cp.async.wait_all;\n" ::);
         __syncthreads();
 
         // ---- Gram matrices of the batches: warp w takes batch w -------------------------------------
@@ -209,10 +239,9 @@ state_update_mma_kernel(const SmParams p) {
 #pragma unroll
             for (int t = 0; t < NT3; ++t) {
                 const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t + ((2 * c) ^ sw));
-                const int m = 8 * t + 2 * c;
-                const double v0 = (m == nens) ? 0.0 : v.x;          // the pseudo-member is not part of y.y
-                const double v1 = (m + 1 == nens) ? 0.0 : v.y;
-                dmma884(g0, g1, v0, v0);
+                // the pseudo-member (last column: t = NT3-1, lane c = 3, second element) is not part of y.y
+                const double v1 = (t == NT3 - 1 && c == 3) ? 0.0 : v.y;
+                dmma884(g0, g1, v.x, v.x);
                 dmma884(h0, h1, v1, v1);
             }
             s_G[b * 64 + n * 8 + 2 * c] = g0 + h0;
@@ -246,9 +275,8 @@ state_update_mma_kernel(const SmParams p) {
 #pragma unroll
                 for (int t = 0; t < NT3; ++t) {
                     const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t + ((2 * c) ^ sw));
-                    const double a0 = (2 * t == jstar) ? 0.0 : x[2 * t];
-                    const double a1 = (2 * t + 1 == jstar) ? 0.0 : x[2 * t + 1];
-                    dmma884(ga0, ga1, a0, v.x);
+                    const double a1 = (t == NT3 - 1 && c == 3) ? 0.0 : x[2 * t + 1];   // mask the mean
+                    dmma884(ga0, ga1, x[2 * t], v.x);
                     dmma884(gb0, gb1, a1, v.y);
                 }
             }
@@ -325,7 +353,7 @@ state_update_mma_kernel(const SmParams p) {
             for (int h = 0; h < 2; ++h) {
                 const int m = 8 * t + 2 * c + h;
                 if (m < nens) p.Xp[row * nens + m] = x[2 * t + h];
-                else if (m == nens) p.xm[row] = x[2 * t + h];
+                else if (m == PC) p.xm[row] = x[2 * t + h];
             }
         }
     }
@@ -348,7 +376,7 @@ static int sm_launch(SmParams &p, cudaStream_t st) {
     p.nlc = (p.nlev + Lc - 1) / Lc;
     p.ntx = (p.nx + btx - 1) / btx;
     const int nty = (p.ny + bty - 1) / bty;
-    const size_t smem = sizeof(double) * ((size_t)SM_Q * YST + SM_ROWS * SM_Q + (SM_Q / 8) * 64 + 3 * SM_ROWS) +
+    const size_t smem = sizeof(double) * ((size_t)SM_Q * YST + SM_ROWS * SM_Q + (SM_Q / 8) * 64 + 3 * SM_ROWS + 6 * SM_Q) +
                         sizeof(int) * (SM_Q + SM_NT + SM_ROWS + SM_NT / 32);
     EXB_CUDA(cudaFuncSetAttribute(state_update_mma_kernel<NT3, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nblocks = (int64_t)p.ntx * nty * p.nlc;
