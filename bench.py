@@ -305,17 +305,21 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     barrier()
     launches0 = _lib.launch_count()
-    if rank == 0:
+    if rank == 0 and not os.environ.get('EXB_NO_CLOCKS'):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
+    marks[0].record()
     phases = {}
-    for _ in range(args.steps):
+    for i in range(args.steps):
         res = step()
+        marks[i + 1].record()
         for k, v in res.ms.items():
             phases[k] = phases.get(k, 0.0) + v / args.steps
     e1.record()
     barrier()
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -391,7 +395,7 @@ def run_ours(args):
                    'bands': bands},
         'state_updates_per_s': state_pairs / (ms_step * 1e-3),
         'state_row_updates': state_pairs, 'obs_assimilated': nassim,
-        'phases_ms': phases,
+        'phases_ms': phases, 'step_ms': step_ms,
         'roofline': {'bound': 'hbm', 'kernel': 'state_update_kernel', 'achieved': achieved, 'peak': hbm_peak,
                      'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                      'note': 'achieved = ALGORITHMIC bytes of the per-observation formulation (sum_k |F_s(k)| * 2 * '

@@ -15,6 +15,13 @@
 //
 // Thread mapping: a row is owned by a group of 8 lanes, lane s holds members s, s+8, ... (MC per lane).
 #include "common.cuh"
+#include <cstring>
+#include <cstdlib>
+
+template <typename T>
+int exb_obs_solve_persistent(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
+                             const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
+                             unsigned long long *counters, cudaStream_t st);
 
 #define PB 64                 // panel width (obs per panel kernel)
 #define GS 8                  // lanes per row
@@ -307,6 +314,16 @@ static int obs_solve_impl(T *Ym, T *Yp, const double *ob_value, const double *ob
         return EXB_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        // preferred: one persistent cooperative kernel (obs_solve_persistent.cu); EXB_OBS_IMPL=launches forces
+        // the kernel-per-panel path below, which is also the fallback when cooperative launch is unavailable
+        const char *impl = getenv("EXB_OBS_IMPL");
+        if (!(impl && strcmp(impl, "launches") == 0)) {
+            const int rc = exb_obs_solve_persistent<T>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, loc_mode,
+                                                       rec, counters, st);
+            if (rc != EXB_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const int mc = (nens + GS - 1) / GS;
 #define EXB_DISPATCH(M) \
     if (mc <= M) return obs_solve_mc<T, M>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, loc_mode, rec, counters, st)
