@@ -32,6 +32,7 @@ SIGNATURES = {
     'exb_recombine_f32': [_p, _p, _i64, _int, _p],
     'exb_obs_solve_f64': [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],
     'exb_obs_solve_f32': [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],
+    'exb_obs_solve_async_status': [],
     'exb_state_update_f64': [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p],
     'exb_state_update_f32': [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p],
     'exb_localization_weights': [_p, _i64, _dbl, _dbl, _dbl, _int, _p, _p, _p],

@@ -281,6 +281,7 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     EXB_CUDA(cudaMemcpyAsync(cnt, dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
     EXB_CUDA(cudaMemcpyAsync(&nex, dnex.p, sizeof(nex), cudaMemcpyDeviceToHost, st));
     EXB_CUDA(cudaStreamSynchronize(st));
+    EXB_TRY(exb_obs_solve_async_status());
     if (stats) {
         float ms[4];
         for (int i = 0; i < 4; ++i) EXB_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));

@@ -19,6 +19,10 @@
 #include <cstdlib>
 
 template <typename T>
+int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
+                      const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
+                      unsigned long long *counters, cudaStream_t st, bool force);
+template <typename T>
 int exb_obs_solve_persistent(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                              const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
                              unsigned long long *counters, cudaStream_t st);
@@ -315,9 +319,19 @@ static int obs_solve_impl(T *Ym, T *Yp, const double *ob_value, const double *ob
     }
     cudaStream_t st = (cudaStream_t)stream;
     {
-        // preferred: one persistent cooperative kernel (obs_solve_persistent.cu); EXB_OBS_IMPL=launches forces
-        // the kernel-per-panel path below, which is also the fallback when cooperative launch is unavailable
+        // EXB_OBS_IMPL = dag | persistent | launches (default: auto)
+        //   dag         dependency-driven solve (obs_solve_dag.cu): the serial chain shrinks to the longest
+        //               dependency path; auto uses it whenever localisation is on and the graph is not dense
+        //   persistent  one cooperative kernel walking panels of 64 obs (obs_solve_persistent.cu); auto's choice
+        //               without localisation, where every ob depends on every earlier one
+        //   launches    kernel-per-panel path below, also the fallback when cooperative launch is unavailable
         const char *impl = getenv("EXB_OBS_IMPL");
+        const bool want_dag = impl ? strcmp(impl, "dag") == 0 : loc_mode == EXB_LOC_GC;
+        if (want_dag) {
+            const int rc = exb_obs_solve_dag<T>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, loc_mode, rec,
+                                                counters, st, impl != nullptr);
+            if (rc != EXB_ERR_UNSUPPORTED) return rc;
+        }
         if (!(impl && strcmp(impl, "launches") == 0)) {
             const int rc = exb_obs_solve_persistent<T>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, loc_mode,
                                                        rec, counters, st);

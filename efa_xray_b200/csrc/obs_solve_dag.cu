@@ -1,0 +1,621 @@
+// Obs-space serial solve as a DEPENDENCY-DRIVEN (sync-free sparse-triangular) kernel.
+//
+// The serial loop of ensrf.py:50-149 restricted to the obs rows is   for k: for j > k:  row_j -= f_kj(row_j . ye_k) ye_k
+// with f_kj = 0 unless ob j lies inside ob k's localisation support (observation.py:117-130).  Ob j therefore
+// depends only on the EARLIER obs whose support reaches it; two obs that are far apart never see each other and
+// the order in which their updates are issued does not matter, as long as every row receives ITS updates in
+// index order.  That is a sparse lower-triangular solve, and it is run like one:
+//   * dag_list_kernel     builds, for every row j, the ascending list of predecessors k < j that may reach it
+//                         (conservative fp32 dot-product test on packed unit vectors; CSR, two passes: count + fill);
+//   * dag_solve_kernel    one WARP per row, rows handed out in index order by a ticket counter.  The warp walks
+//                         its predecessor list in order; for each k it needs the published record of ob k
+//                         (ye_k and the scalars innov_k, c1_k, beta_k), applies the rank-1 update
+//                         (ensrf.py:95-141) to its row, and after the last predecessor computes its own scalars
+//                         (ensrf.py:61-91, :135) and publishes its record.
+// The serial chain is no longer Nobs steps long but the longest dependency path (config 3: 3 864 instead of
+// 100 000), and thousands of rows are in flight at once.  The result is the same arithmetic in the same order for
+// every row, i.e. the serial order of the reference is preserved exactly.
+//
+// Publication without flags or fences: records go to a side buffer P (row stride 32*MC elements) / S (2 doubles
+// per ob) that is pre-filled with an all-ones bit pattern (a NaN the arithmetic never produces; the writer
+// canonicalises).  A reader loads the record with gpu-scope relaxed loads and accepts it when no word is the
+// sentinel; each lane checks exactly the words it consumes, each word is written by one aligned store, so no
+// ordering between words is needed.  Waiting warps poll one 16-byte word of S with back-off.
+// Deadlock freedom: a warp only waits for rows with a lower ticket, and those were taken by warps that are
+// already running.  A watchdog turns a would-be hang into an error status.
+#include "common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define DG_TILE 2048            // candidates staged in shared memory per step of the list builder
+#define DG_LWARPS 4             // warps per CTA of the list builder
+#define DG_LROWS (32 * DG_LWARPS) // rows per CTA of the list builder (one lane per row)
+#define DG_WARPS 4              // warps per CTA of the solve kernel
+#define DG_MINBLOCKS 8          // -> at most 64 registers per thread, 32 rows in flight per SM
+#define DG_SENT 0xFFFFFFFFFFFFFFFFull
+#define DG_FULL 0xffffffffu
+#define DG_WATCHDOG (1u << 24)  // polls (>= 100 ns each once backed off) before a wait is declared dead
+
+template <typename T>
+int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
+                      const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
+                      unsigned long long *counters, cudaStream_t st, bool force);
+
+__device__ __forceinline__ int64_t ceil_div64_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// ------------------------------------------------------------------------------------------
+// predecessor lists
+// ------------------------------------------------------------------------------------------
+// float4 per ob: unit vector and, in .w, the smallest u_j . u_k at which row j is still inside the support of
+// THIS ob acting as k (squared chord = 2 - 2 dot), lowered so that the fp32 test never misses a pair the fp64
+// weight would keep; > 1 for obs that are not assimilated (never a predecessor).
+__global__ void dag_pack_kernel(const double *__restrict__ geo, const uint8_t *__restrict__ assim, int64_t nobs,
+                                int loc_mode, float4 *__restrict__ pk) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nobs) return;
+    float4 q;
+    q.x = (float)geo[GEO_UX * nobs + k];
+    q.y = (float)geo[GEO_UY * nobs + k];
+    q.z = (float)geo[GEO_UZ * nobs + k];
+    float cmin = 3.0f;
+    if (assim[k]) {
+        const double amax = geo[GEO_AMAX * nobs + k];
+        if (loc_mode != EXB_LOC_GC || amax >= 1.0) cmin = -3.0f;
+        else {
+            // weight != 0 needs a < amax, i.e. squared chord 4a < 4 amax.  The fp32 dot of two rounded unit
+            // vectors is within ~4e-7 of the exact one: 2e-6 on the squared chord covers it with room.
+            cmin = __double2float_rd(1.0 - 0.5 * (4.0 * amax + 2e-6));
+        }
+    }
+    q.w = cmin;
+    pk[k] = q;
+}
+
+// FILL = false: cnt[j] = number of candidates k < j of row j.  FILL = true: list[off[j] - list_base ...] = them,
+// ascending.  One LANE per row: a warp owns 32 consecutive rows and walks the staged candidates one at a time
+// (a broadcast shared-memory read), so every lane meets its row's predecessors in ascending order and appends
+// them without any cross-lane prefix.  CTA = DG_LROWS consecutive rows; candidate tiles are staged once per CTA.
+template <bool FILL>
+__global__ void __launch_bounds__(DG_LWARPS * 32)
+dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_end, int *__restrict__ cnt,
+                const int64_t *__restrict__ off, int64_t list_base, int *__restrict__ list) {
+    __shared__ float4 tile[DG_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Row block b costs ~b: a CTA takes block blockIdx.x and its mirror image, so every CTA has the same work.
+    const int64_t nblk = ceil_div64_dev(row_end - row_begin, DG_LROWS);
+    for (int half = 0; half < 2; ++half) {
+    const int64_t blk = half == 0 ? (int64_t)blockIdx.x : nblk - 1 - (int64_t)blockIdx.x;
+    if (half == 1 && blk <= (int64_t)blockIdx.x) break;
+    const int64_t j0 = row_begin + blk * DG_LROWS;
+    const int64_t jw = j0 + warp * 32;                                // first row of this warp
+    const int64_t j = jw + lane;
+    const bool valid = j < row_end;
+    const int64_t jtop = (j0 + DG_LROWS < row_end ? j0 + DG_LROWS : row_end) - 1;    // last row of this CTA
+    const float qnan = __int_as_float(0x7fc00000);                    // rows past the end: every test is false
+    float4 me = make_float4(qnan, qnan, qnan, 0.f);
+    if (valid) me = pk[j];
+    int *out = list;
+    if (FILL && valid) out = list + (off[j] - list_base);
+    int count = 0;
+    for (int64_t t0 = 0; t0 < jtop; t0 += DG_TILE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < DG_TILE; i += DG_LWARPS * 32) {
+            const int64_t k = t0 + i;
+            tile[i] = (k < jtop) ? pk[k] : make_float4(0.f, 0.f, 0.f, 3.0f);
+        }
+        __syncthreads();
+        if (jw >= row_end) continue;
+        // candidates k < jw precede every row of the warp
+        const int64_t rem = jw - t0;
+        const int full = rem <= 0 ? 0 : (rem < DG_TILE ? (int)rem : DG_TILE);
+#pragma unroll 8
+        for (int i = 0; i < full; ++i) {
+            const float4 q = tile[i];
+            const float dot = fmaf(me.x, q.x, fmaf(me.y, q.y, me.z * q.z));
+            if (dot >= q.w) {
+                if (FILL) out[count] = (int)(t0 + i);
+                ++count;
+            }
+        }
+        // the warp's own 32 rows: k < j per lane
+        const int64_t last = jw + 31 - t0;
+        const int lim = last < DG_TILE ? (int)last : DG_TILE;
+        for (int i = full; i < lim; ++i) {
+            const float4 q = tile[i];
+            const float dot = fmaf(me.x, q.x, fmaf(me.y, q.y, me.z * q.z));
+            if (t0 + i < j && dot >= q.w) {
+                if (FILL) out[count] = (int)(t0 + i);
+                ++count;
+            }
+        }
+    }
+    if (!FILL && valid) cnt[j] = count;
+    }
+}
+
+// exclusive prefix sum of cnt[n] into off[n+1] (one CTA walking coalesced chunks of 1024; n is ~1e5..1e6)
+__global__ void __launch_bounds__(1024) dag_scan_kernel(const int *__restrict__ cnt, int64_t n, int64_t *__restrict__ off) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n; b += 1024) {
+        const int64_t i = b + t;
+        const long long v = (i < n) ? cnt[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(DG_FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(DG_FULL, w, o);
+                if (lane >= o) w += y;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        const long long excl = carry + (warp ? wsum[warp - 1] : 0) + x - v;
+        if (i < n) off[i] = excl;
+        __syncthreads();
+        if (t == 1023) carry_s = carry + wsum[31];
+        __syncthreads();
+    }
+    if (t == 0) off[n] = carry_s;
+}
+
+// ------------------------------------------------------------------------------------------
+// the solve
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct DgArgs {
+    T *Ym;
+    T *Yp;
+    const double *ob_value;
+    const double *ob_error;
+    const uint8_t *ob_assim;
+    const double *geo;
+    double *rec;
+    unsigned long long *counters;
+    const int64_t *off;
+    const int *list;
+    int64_t list_base;
+    T *P;                        // published ye rows, stride 32*MC, sentinel-initialised
+    double *S;                   // published scalars [nobs][2] = c1*innov, c1*beta; sentinel-initialised
+    int *ticket;
+    int *status;                 // != 0: watchdog fired
+    int64_t nobs, row_begin, row_end;
+    int nens, loc_mode;
+};
+
+__device__ __forceinline__ void dg_ld16(const void *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void dg_st16(void *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+// 256-bit accesses (sm_100): one instruction per 32-byte sector
+__device__ __forceinline__ void dg_ld32(const void *p, unsigned long long &a, unsigned long long &b, unsigned long long &c,
+                                        unsigned long long &d) {
+    asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void dg_st32(void *p, unsigned long long a, unsigned long long b, unsigned long long c,
+                                        unsigned long long d) {
+    asm volatile("st.relaxed.gpu.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// The sentinel is recognised by 32 bits per element: the high half of a double / the whole float equal to
+// 0xFFFFFFFF (a NaN either way; the writer replaces such a value by the canonical quiet NaN).
+__device__ __forceinline__ unsigned dg_hi(unsigned long long w) { return (unsigned)(w >> 32); }
+__device__ __forceinline__ unsigned dg_lo(unsigned long long w) { return (unsigned)w; }
+
+template <typename T> struct DgWord;
+template <> struct DgWord<double> {
+    static constexpr int PER = 1;                                    // elements per 64-bit word
+    static __device__ __forceinline__ bool pending(unsigned long long w) { return dg_hi(w) == 0xFFFFFFFFu; }
+    static __device__ __forceinline__ void unpack(unsigned long long w, double *o) { o[0] = __longlong_as_double((long long)w); }
+    static __device__ __forceinline__ unsigned long long pack(const double *v) {
+        const unsigned long long w = (unsigned long long)__double_as_longlong(v[0]);
+        return dg_hi(w) == 0xFFFFFFFFu ? 0x7FF8000000000000ull : w;
+    }
+};
+template <> struct DgWord<float> {
+    static constexpr int PER = 2;
+    static __device__ __forceinline__ bool pending(unsigned long long w) {
+        return dg_lo(w) == 0xFFFFFFFFu || dg_hi(w) == 0xFFFFFFFFu;
+    }
+    static __device__ __forceinline__ void unpack(unsigned long long w, float *o) {
+        o[0] = __uint_as_float(dg_lo(w));
+        o[1] = __uint_as_float(dg_hi(w));
+    }
+    static __device__ __forceinline__ unsigned long long pack(const float *v) {
+        unsigned lo = __float_as_uint(v[0]), hi = __float_as_uint(v[1]);
+        if (lo == 0xFFFFFFFFu) lo = 0x7FC00000u;
+        if (hi == 0xFFFFFFFFu) hi = 0x7FC00000u;
+        return (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+};
+__device__ __forceinline__ unsigned long long dg_pack_scalar(double v) {
+    const unsigned long long w = (unsigned long long)__double_as_longlong(v);
+    return dg_hi(w) == 0xFFFFFFFFu ? 0x7FF8000000000000ull : w;
+}
+
+__device__ __forceinline__ double dg_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DG_FULL, v, o);
+    return v;
+}
+
+// One published record as held by a lane: NW 64-bit words of the ye row + the two scalars
+// s[0] = c1*innov (mean gain per unit weight*dot), s[1] = c1*beta (perturbation factor per unit weight*dot).
+template <int NW>
+struct DgRec {
+    unsigned long long w[NW];
+    unsigned long long s[2];
+};
+
+template <typename T, int MC>
+struct DgCfg {
+    static constexpr int NW = MC / DgWord<T>::PER;                   // 64-bit words per lane
+    static_assert(NW >= 2 && NW % 2 == 0, "a lane must own whole 16-byte chunks");
+};
+
+template <typename T, int MC>
+__device__ __forceinline__ void dg_fetch(const DgArgs<T> &a, int k, int lane, DgRec<DgCfg<T, MC>::NW> &r) {
+    constexpr int NW = DgCfg<T, MC>::NW;
+    const unsigned long long *p = reinterpret_cast<const unsigned long long *>(a.P + ((int64_t)k * 32 + lane) * MC);
+    if (lane * MC >= a.nens) {                    // pad lane: nothing to read, never pending
+#pragma unroll
+        for (int c = 0; c < NW; ++c) r.w[c] = 0ull;
+    } else if constexpr (NW % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < NW; c += 4) dg_ld32(p + c, r.w[c], r.w[c + 1], r.w[c + 2], r.w[c + 3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NW; c += 2) dg_ld16(p + c, r.w[c], r.w[c + 1]);
+    }
+    dg_ld16(a.S + (int64_t)k * 2, r.s[0], r.s[1]);
+}
+
+template <typename T, int MC>
+__device__ __forceinline__ bool dg_ready(const DgRec<DgCfg<T, MC>::NW> &r) {
+    constexpr int NW = DgCfg<T, MC>::NW;
+    bool ok = (dg_hi(r.s[0]) != 0xFFFFFFFFu) && (dg_hi(r.s[1]) != 0xFFFFFFFFu);
+#pragma unroll
+    for (int c = 0; c < NW; ++c) ok = ok && !DgWord<T>::pending(r.w[c]);
+    return __all_sync(DG_FULL, ok);
+}
+
+// Waits until the polled word of ob k's record has been written.  Returns false when the watchdog fired (here
+// or elsewhere).  Takes no reference to the caller's record so that it stays in registers.
+__device__ __noinline__ bool dg_wait(const double *S, int *status, int k, int lane) {
+    const double *s = S + (int64_t)k * 2;
+    unsigned polls = 0;
+    while (true) {
+        unsigned long long b0, b1;
+        dg_ld16(s, b0, b1);
+        if (dg_hi(b1) != 0xFFFFFFFFu) return true;
+        ++polls;
+        if (polls > 1) __nanosleep(polls < 8 ? 50 : (polls < 32 ? 200 : 500));
+        if ((polls & 1023u) == 0) {
+            if (*reinterpret_cast<volatile int *>(status) != 0) return false;
+            if (polls >= DG_WATCHDOG) {
+                if (lane == 0) atomicExch(status, 1);
+                return false;
+            }
+        }
+    }
+}
+
+// Per-row state of a warp while it walks its predecessor list.
+template <typename T, int MC>
+struct DgRow {
+    T x[MC];
+    double mj;
+    int kl;             // this lane's list entry of the current batch
+    double wl;          // and its weight
+    unsigned m;         // entries of the batch still to apply
+    int k;              // ob whose record is in `cur`
+    double w;
+    bool dead;
+};
+
+// One step of the pipelined walk: `cur` holds (maybe incompletely) the record of ob r.k.  Makes it complete,
+// starts the fetch of the next entry into `nxt`, applies cur.  Returns false when the batch is exhausted (or dead).
+template <typename T, int MC>
+__device__ __forceinline__ bool dg_step(const DgArgs<T> &a, int lane, DgRow<T, MC> &r, DgRec<DgCfg<T, MC>::NW> &cur,
+                                        DgRec<DgCfg<T, MC>::NW> &nxt) {
+    constexpr int NW = DgCfg<T, MC>::NW;
+    constexpr int PER = DgWord<T>::PER;
+    while (!dg_ready<T, MC>(cur)) {
+        if (!dg_wait(a.S, a.status, r.k, lane)) { r.dead = true; return false; }
+        dg_fetch<T, MC>(a, r.k, lane, cur);
+    }
+    const bool more = r.m != 0;
+    const double w = r.w;
+    if (more) {                                   // speculative: re-fetched at its turn if not complete yet
+        const int i = __ffs(r.m) - 1;
+        r.m &= r.m - 1;
+        r.k = __shfl_sync(DG_FULL, r.kl, i);
+        r.w = __shfl_sync(DG_FULL, r.wl, i);
+        dg_fetch<T, MC>(a, r.k, lane, nxt);
+    }
+    // rank-1 update of this row by the ob in cur   (ensrf.py:95, :115-119, :130, :135-141)
+    T ye[MC];
+#pragma unroll
+    for (int c = 0; c < NW; ++c) DgWord<T>::unpack(cur.w[c], ye + c * PER);
+    T d0 = 0, d1 = 0;
+#pragma unroll
+    for (int q = 0; q < MC; q += 2) {
+        d0 += r.x[q] * ye[q];
+        d1 += r.x[q + 1] * ye[q + 1];
+    }
+    const double wd = w * dg_warp_sum((double)(d0 + d1));                 // loc * (row . ye)
+    r.mj += wd * __longlong_as_double((long long)cur.s[0]);                // + kmat * innov
+    const T f = (T)(wd * __longlong_as_double((long long)cur.s[1]));       // beta * kmat
+#pragma unroll
+    for (int q = 0; q < MC; ++q) r.x[q] -= f * ye[q];
+    return more;
+}
+
+template <typename T, int MC>
+__global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(const DgArgs<T> a) {
+    constexpr int NW = DgCfg<T, MC>::NW;
+    constexpr int PER = DgWord<T>::PER;
+    const int lane = threadIdx.x & 31;
+    const int64_t nobs = a.nobs;
+    const int nens = a.nens;
+    const double inv_n = 1.0 / (double)nens;
+    const bool gc = a.loc_mode == EXB_LOC_GC;
+    unsigned long long npairs = 0;
+
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1);
+        t = __shfl_sync(DG_FULL, t, 0);
+        const int64_t j = a.row_begin + t;
+        if (j >= a.row_end) break;
+
+        // ---- this row: perturbations (lane owns members [MC*lane, MC*lane+MC)), mean, geometry ----
+        DgRow<T, MC> r;
+#pragma unroll
+        for (int i = 0; i < MC; ++i) {
+            const int m = lane * MC + i;
+            r.x[i] = (m < nens) ? __ldcg(a.Yp + j * nens + m) : (T)0;
+        }
+        r.mj = (double)__ldcg(a.Ym + j);
+        r.dead = false;
+        const double ux = a.geo[GEO_UX * nobs + j], uy = a.geo[GEO_UY * nobs + j], uz = a.geo[GEO_UZ * nobs + j];
+        const int64_t lb = a.off[j] - a.list_base, le = a.off[j + 1] - a.list_base;
+
+        // ---- predecessors, 32 at a time: weights lane-parallel, updates strictly in list order ----
+        int kl_next = (lb + lane < le) ? __ldg(a.list + lb + lane) : -1;
+        for (int64_t base = lb; base < le; base += 32) {
+            r.kl = kl_next;
+            kl_next = (base + 32 + lane < le) ? __ldg(a.list + base + 32 + lane) : -1;
+            r.wl = 0.0;
+            if (r.kl >= 0) {
+                r.wl = 1.0;
+                if (gc)
+                    r.wl = loc_weight(hav_a(ux, uy, uz, __ldg(a.geo + GEO_UX * nobs + r.kl), __ldg(a.geo + GEO_UY * nobs + r.kl),
+                                            __ldg(a.geo + GEO_UZ * nobs + r.kl)),
+                                      __ldg(a.geo + GEO_INVHW * nobs + r.kl), __ldg(a.geo + GEO_AMAX * nobs + r.kl));
+            }
+            r.m = __ballot_sync(DG_FULL, r.wl != 0.0);
+            if (!r.m) continue;
+            if (lane == 0) npairs += __popc(r.m);
+            DgRec<NW> ra, rb;
+            const int i = __ffs(r.m) - 1;
+            r.m &= r.m - 1;
+            r.k = __shfl_sync(DG_FULL, r.kl, i);
+            r.w = __shfl_sync(DG_FULL, r.wl, i);
+            dg_fetch<T, MC>(a, r.k, lane, ra);
+            while (true) {                        // ping-pong between the two record buffers
+                if (!dg_step<T, MC>(a, lane, r, ra, rb)) break;
+                if (!dg_step<T, MC>(a, lane, r, rb, ra)) break;
+            }
+            if (r.dead) break;
+        }
+        if (r.dead) break;
+
+        // ---- this ob's own step: ensrf.py:61-91, :135, :144-149 ----
+        double s0 = 0.0, q0 = 0.0;
+#pragma unroll
+        for (int q = 0; q < MC; ++q) { const double v = (double)r.x[q]; s0 += v; q0 += v * v; }
+        const double rs = dg_warp_sum(s0), rq = dg_warp_sum(q0);
+        const double my_val = a.ob_value[j], my_err = a.ob_error[j];
+        const bool act = a.ob_assim[j] != 0;
+        const double mj = r.mj;
+        const double mean = rs * inv_n;
+        const double varye = fmax(rq * inv_n - mean * mean, 0.0);                    // np.var, ddof 0
+        const double innov = my_val - mj;
+        const double kdenom = varye + my_err;
+        const double c1 = 1.0 / ((double)(nens - 1) * kdenom);
+        const double beta = 1.0 / (1.0 + sqrt(my_err) * rsqrt(kdenom));              // 1/(1+sqrt(R/kdenom))
+
+        // publish (data first, the polled word last); skipped obs are never anyone's predecessor
+        if (act) {
+            unsigned long long *p = reinterpret_cast<unsigned long long *>(a.P + (j * 32 + lane) * MC);
+            unsigned long long pw[NW];
+            if (lane * MC < nens) {
+#pragma unroll
+            for (int c = 0; c < NW; ++c) pw[c] = DgWord<T>::pack(r.x + c * PER);
+            if constexpr (NW % 4 == 0) {
+#pragma unroll
+                for (int c = 0; c < NW; c += 4) dg_st32(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NW; c += 2) dg_st16(p + c, pw[c], pw[c + 1]);
+            }
+            }
+            if (lane == 0) dg_st16(a.S + j * 2, dg_pack_scalar(c1 * innov), dg_pack_scalar(c1 * beta));
+        }
+        // outputs of the C ABI: ye_j / mye_j in place, per-ob records
+#pragma unroll
+        for (int i = 0; i < MC; ++i) {
+            const int mm = lane * MC + i;
+            if (mm < nens) a.Yp[j * nens + mm] = r.x[i];
+        }
+        if (lane == 0) {
+            a.Ym[j] = (T)mj;
+            a.rec[REC_PRIOR_MEAN * nobs + j] = mj;                                   // ensrf.py:66
+            a.rec[REC_PRIOR_VAR * nobs + j] = varye;                                 // ensrf.py:70
+            a.rec[REC_INNOV * nobs + j] = innov;
+            a.rec[REC_C1 * nobs + j] = c1;
+            a.rec[REC_BETA * nobs + j] = beta;
+            a.rec[REC_ASSIM * nobs + j] = act ? 1.0 : 0.0;
+            if (act) {
+                // the ob's own row: weight at distance 0, kcov = ye.ye/(N-1)   (ensrf.py:144-147)
+                const double wself = gc ? loc_weight(0.0, a.geo[GEO_INVHW * nobs + j], a.geo[GEO_AMAX * nobs + j]) : 1.0;
+                const double kmat = wself * rq * c1;
+                const double shrink = 1.0 - beta * kmat;
+                a.rec[REC_POST_MEAN * nobs + j] = mj + kmat * innov;
+                a.rec[REC_POST_VAR * nobs + j] = varye * shrink * shrink;
+                if (wself != 0.0) npairs++;
+            } else {
+                a.rec[REC_POST_MEAN * nobs + j] = nan("");
+                a.rec[REC_POST_VAR * nobs + j] = nan("");
+            }
+        }
+    }
+    if (a.counters && lane == 0 && npairs) atomicAdd(&a.counters[0], npairs);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+namespace {
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit AsyncBuf(cudaStream_t s) : st(s) {}
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    template <typename U> U *as() { return static_cast<U *>(p); }
+};
+int *g_status_host = nullptr;     // pinned, mapped: the watchdog's verdict, readable without a device sync
+int *g_status_dev = nullptr;
+}   // namespace
+
+// Status of the asynchronous part of the last exb_obs_solve_* on this process: 0 ok, 1 = the dependency wait
+// watchdog fired (results are invalid).  Call after synchronising the stream.
+extern "C" int exb_obs_solve_async_status(void) {
+    if (!g_status_host) return 0;
+    const int v = *reinterpret_cast<volatile int *>(g_status_host);
+    if (v == 0) return EXB_OK;
+    exb_set_error("exb_obs_solve: a dependency wait never completed (watchdog); the obs-space records are invalid");
+    return EXB_ERR_CUDA;
+}
+
+template <typename T, int MC>
+static int dg_run(DgArgs<T> a, const float4 *pk, const std::vector<int64_t> &off_h, int64_t budget, cudaStream_t st) {
+    int dev = 0, sms = 0, per_sm = 0;
+    EXB_CUDA(cudaGetDevice(&dev));
+    EXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    EXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag_solve_kernel<T, MC>, DG_WARPS * 32, 0));
+    if (per_sm < 1) return EXB_ERR_UNSUPPORTED;
+    const int64_t nobs = a.nobs;
+    AsyncBuf P(st), S(st), list(st), ticket(st);
+    const size_t p_bytes = (size_t)nobs * 32 * MC * sizeof(T), s_bytes = (size_t)nobs * 2 * sizeof(double);
+    EXB_CUDA(P.alloc(p_bytes));
+    EXB_CUDA(S.alloc(s_bytes));
+    EXB_CUDA(cudaMemsetAsync(P.p, 0xFF, p_bytes, st));
+    EXB_CUDA(cudaMemsetAsync(S.p, 0xFF, s_bytes, st));
+    EXB_CUDA(ticket.alloc(sizeof(int)));
+    a.P = P.as<T>();
+    a.S = S.as<double>();
+    a.ticket = ticket.as<int>();
+    // row blocks whose predecessor lists fit the budget
+    int64_t r0 = 0, max_block = 0;
+    std::vector<std::pair<int64_t, int64_t>> blocks;
+    while (r0 < nobs) {
+        int64_t r1 = r0 + 1;
+        while (r1 < nobs && off_h[r1 + 1] - off_h[r0] <= budget) ++r1;
+        blocks.push_back({r0, r1});
+        if (off_h[r1] - off_h[r0] > max_block) max_block = off_h[r1] - off_h[r0];
+        r0 = r1;
+    }
+    EXB_CUDA(list.alloc((size_t)max_block * sizeof(int)));
+    a.list = list.as<int>();
+    for (auto &b : blocks) {
+        a.row_begin = b.first;
+        a.row_end = b.second;
+        a.list_base = off_h[b.first];
+        const int64_t nrows = b.second - b.first;
+        if (off_h[b.second] > off_h[b.first]) {
+            dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+                pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>());
+            exb_count_launches(1);
+        }
+        EXB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(int), st));
+        int64_t grid = (int64_t)sms * per_sm;
+        const int64_t need = ceil_div64(nrows, DG_WARPS);
+        if (grid > need) grid = need;
+        dag_solve_kernel<T, MC><<<(unsigned)grid, DG_WARPS * 32, 0, st>>>(a);
+        exb_count_launches(1);
+    }
+    return exb_check_launch("dag_solve_kernel");
+}
+
+// force = false: returns EXB_ERR_UNSUPPORTED when the dependency graph is too dense for this method to pay
+// (the caller then uses the panel kernel).
+template <typename T>
+int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
+                      const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
+                      unsigned long long *counters, cudaStream_t st, bool force) {
+    if (nobs >= 0x7fffffff) return EXB_ERR_UNSUPPORTED;
+    if (!g_status_host) {
+        // work buffers come from the stream-ordered pool; keep freed blocks cached instead of returning them to
+        // the driver at every synchronisation (a 0.5 GB list costs ~20 ms to re-allocate otherwise)
+        int dev = 0;
+        cudaMemPool_t pool;
+        EXB_CUDA(cudaGetDevice(&dev));
+        EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        EXB_CUDA(cudaHostAlloc(&g_status_host, sizeof(int), cudaHostAllocMapped));
+        EXB_CUDA(cudaHostGetDevicePointer(&g_status_dev, g_status_host, 0));
+    }
+    *g_status_host = 0;
+    AsyncBuf pk(st), cnt(st), off(st);
+    EXB_CUDA(pk.alloc((size_t)nobs * sizeof(float4)));
+    EXB_CUDA(cnt.alloc((size_t)nobs * sizeof(int)));
+    EXB_CUDA(off.alloc((size_t)(nobs + 1) * sizeof(int64_t)));
+    dag_pack_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(geo, ob_assim, nobs, loc_mode, pk.as<float4>());
+    dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+        pk.as<float4>(), 0, nobs, cnt.as<int>(), nullptr, 0, nullptr);
+    dag_scan_kernel<<<1, 1024, 0, st>>>(cnt.as<int>(), nobs, off.as<int64_t>());
+    exb_count_launches(3);
+    EXB_CUDA(cudaGetLastError());
+    std::vector<int64_t> off_h((size_t)nobs + 1);
+    EXB_CUDA(cudaMemcpyAsync(off_h.data(), off.p, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    EXB_CUDA(cudaStreamSynchronize(st));
+    const double nnz = (double)off_h[(size_t)nobs];
+    const double dense = 0.5 * (double)nobs * (double)(nobs - 1);
+    if (!force && nobs > 2048 && nnz > 0.5 * dense) return EXB_ERR_UNSUPPORTED;
+    int64_t budget = (int64_t)1 << 30;                                  // list entries per row block (4 GiB)
+    if (const char *e = getenv("EXB_DAG_BUDGET")) {
+        const long long v = atoll(e);
+        if (v > 0) budget = v;
+    }
+    DgArgs<T> a;
+    a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
+    a.counters = counters; a.off = off.as<int64_t>(); a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
+    a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
+    a.loc_mode = loc_mode;
+    if (nens <= 128) return dg_run<T, 4>(a, pk.as<float4>(), off_h, budget, st);
+    if (nens <= 256) return dg_run<T, 8>(a, pk.as<float4>(), off_h, budget, st);
+    return EXB_ERR_UNSUPPORTED;
+}
+
+template int exb_obs_solve_dag<double>(double *, double *, const double *, const double *, const uint8_t *, const double *,
+                                       int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool);
+template int exb_obs_solve_dag<float>(float *, float *, const double *, const double *, const uint8_t *, const double *,
+                                      int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool);

@@ -272,6 +272,7 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
         tm.mark('recombine')
         rec_h = rec.cpu().numpy()
+        _lib.call('exb_obs_solve_async_status')
         cnt = counters.cpu().numpy()
         nex_h = int(nex.item())
     return AnalysisResult(prior_mean=rec_h[0], prior_var=rec_h[1], post_mean=rec_h[2], post_var=rec_h[3],

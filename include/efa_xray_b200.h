@@ -131,13 +131,22 @@ int exb_recombine_f32(float *X, const float *xm, int64_t nrows, int nens, void *
  *   out: Yp[k][:] = ye_k, the ensemble of ob k as read when ob k is processed (ensrf.py:64);
  *        Ym[k]    = mye_k (ensrf.py:63);  rec = per-ob records (see top).
  * counters (device uint64[2], may be NULL): [0] += number of (ob k, obs row j >= k) pairs with
- * non-zero localisation weight = sum_k |F_o(k)| of SURVEY.md section 8d. */
+ * non-zero localisation weight = sum_k |F_o(k)| of SURVEY.md section 8d.
+ * Three implementations with identical results up to summation order (environment EXB_OBS_IMPL = dag |
+ * persistent | launches; default: dag with localisation, persistent without): see DESIGN.md section 4.2. */
 int exb_obs_solve_f64(double *Ym, double *Yp, const double *ob_value, const double *ob_error,
                       const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
                       int loc_mode, double *rec, unsigned long long *counters, void *stream);
 int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, const double *ob_error,
                       const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
                       int loc_mode, double *rec, unsigned long long *counters, void *stream);
+
+/* exb_obs_solve_* only enqueues its kernels (the dependency-driven variant synchronises the stream once, to size
+ * its work lists, before the solve itself is launched).  Its kernels wait on each other inside the launch; a
+ * watchdog ends a wait that can never be satisfied (corrupted inputs) instead of hanging the device.  After
+ * synchronising the stream, this returns EXB_OK, or EXB_ERR_CUDA if the watchdog fired during the last
+ * exb_obs_solve_* of this process (its outputs are then invalid). */
+int exb_obs_solve_async_status(void);
 
 /* State sweep over one latitude-band shard: applies obs [ob_begin, ob_end) in serial order to every
  * state row of the shard -- kcov, localisation, gain, mean update and square-root perturbation update

@@ -242,3 +242,86 @@ def test_rectilinear_search_is_bit_identical_to_brute_force():
         assert torch.equal(i_r, i_g)
         assert torch.equal(w_r, w_g)
         assert int(n_r.item()) == int(n_g.item())
+
+
+def _obs_block(case, dtype='f64'):
+    """Device-side inputs of exb_obs_solve_* for a Case: ob priors H.x split into mean + perturbations."""
+    import torch
+    from efa_xray_b200 import engine
+    dev = torch.device('cuda', 0)
+    tdt = torch.float64 if dtype == 'f64' else torch.float32
+    X = torch.as_tensor(case.to_vect()).to(dev).to(tdt).contiguous()
+    ny, nx = case.lat2d.shape
+    nt = len(case.times)
+    tlo, thi, wlo, whi, _ = engine.time_weights(case.times, case.ob_time)
+    obs = engine.ObsArrays(value=case.ob_value, error=case.ob_error, lat=case.ob_lat, lon=case.ob_lon,
+                           halfwidth=case.ob_halfwidth, assimilate=case.ob_assimilate.astype(np.uint8),
+                           row0=(case.ob_var * nt + tlo) * (ny * nx), row1=(case.ob_var * nt + thi) * (ny * nx),
+                           tw0=wlo, tw1=whi)
+    grid = engine.GridTables(case.lat2d, case.lon2d, dev)
+    Yp, _ = engine.ob_priors(X, grid, obs, dtype)
+    Ym = torch.empty(obs.nobs, dtype=tdt, device=dev)
+    from efa_xray_b200 import _lib
+    _lib.call('exb_split_mean_pert_' + dtype, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, X.shape[1], _lib.stream_ptr())
+    return obs, Ym, Yp
+
+
+def _run_obs_solve(obs, Ym, Yp, loc_mode, impl, dtype='f64', budget=None):
+    import os
+    import torch
+    from efa_xray_b200 import engine, _lib
+    dev = Yp.device
+    obs_dev, geo = engine.upload_obs(obs, dev, loc_mode)
+    ym, yp = Ym.clone(), Yp.clone()
+    rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    old = {k: os.environ.get(k) for k in ('EXB_OBS_IMPL', 'EXB_DAG_BUDGET')}
+    os.environ['EXB_OBS_IMPL'] = impl
+    if budget is not None:
+        os.environ['EXB_DAG_BUDGET'] = str(budget)
+    try:
+        engine.obs_solve(ym, yp, obs_dev, geo, Yp.shape[1], loc_mode, rec, counters, dtype)
+        torch.cuda.synchronize()
+        _lib.call('exb_obs_solve_async_status')
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return ym.cpu().numpy(), yp.cpu().numpy(), rec.cpu().numpy(), int(counters[0].item())
+
+
+@pytest.mark.parametrize('kw,loc_mode', [
+    (dict(ny=46, nx=90, nmem=50, nobs=700, cutoff_km=2500.0, seed=31, frac_skip=0.05, mixed_radius=True), 1),
+    (dict(ny=46, nx=90, nmem=100, nobs=3000, cutoff_km=800.0, seed=32, mixed_error=True), 1),
+    (dict(ny=37, nx=72, nmem=130, nobs=300, cutoff_km=3000.0, seed=33, frac_skip=0.1), 1),
+    (dict(ny=37, nx=72, nmem=20, nobs=200, seed=34), 0),
+])
+def test_obs_solve_variants_agree(kw, loc_mode):
+    """The dependency-driven obs-space solve, the persistent panel kernel and the kernel-per-panel path evolve
+    the same closed obs-row subsystem in the same serial order: records, ye rows,
+    diagnostics and pair counts must agree; the dependency-driven one also when its predecessor lists are
+    cut into many row blocks."""
+    case = make_case(**kw)
+    obs, Ym, Yp = _obs_block(case)
+    ref = _run_obs_solve(obs, Ym, Yp, loc_mode, 'launches')
+    runs = [_run_obs_solve(obs, Ym, Yp, loc_mode, 'persistent'), _run_obs_solve(obs, Ym, Yp, loc_mode, 'dag'),
+            _run_obs_solve(obs, Ym, Yp, loc_mode, 'dag', budget=997)]
+    scale = np.abs(ref[1]).max()
+    for ym, yp, rec, npairs in runs:
+        assert npairs == ref[3]
+        np.testing.assert_allclose(ym, ref[0], rtol=1e-11)
+        assert np.abs(yp - ref[1]).max() <= 1e-11 * scale
+        np.testing.assert_allclose(rec, ref[2], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_obs_solve_dag_fp32():
+    case = make_case(ny=46, nx=90, nmem=50, nobs=500, cutoff_km=2500.0, seed=35)
+    obs, Ym, Yp = _obs_block(case, 'f32')
+    ref = _run_obs_solve(obs, Ym, Yp, 1, 'persistent', 'f32')
+    ym, yp, rec, npairs = _run_obs_solve(obs, Ym, Yp, 1, 'dag', 'f32')
+    assert npairs == ref[3]
+    np.testing.assert_allclose(ym, ref[0], rtol=1e-5)
+    assert np.abs(yp - ref[1]).max() <= 2e-4 * np.abs(ref[1]).max()
+    np.testing.assert_allclose(rec[:4], ref[2][:4], rtol=2e-3, equal_nan=True)
