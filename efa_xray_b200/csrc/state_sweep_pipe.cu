@@ -1,0 +1,629 @@
+// State sweep, warp-specialised FP64 tensor-core version (production path for float64 states).
+//
+// Same mathematics as state_update_mma.cu (read its header first: blocked 8-ob form of ensrf.py:95-141 on
+// mma.sync.m8n8k4.f64, mean carried as a pseudo-member column), different organisation.  That kernel kept
+// the FP64 tensor pipe busy only half of the time: every round of 64 candidates was scanned, staged and
+// weighted by the same warps that then issue the DMMAs, behind CTA-wide barriers.  Here
+//   * one CTA per SM = 12 CONSUMER warps (8 state rows each = 96 rows of one patch, in registers for the
+//     whole launch) + 4 PRODUCER warps;
+//   * producers find the patch's candidate obs in serial order (fp32 cap test over the candidate list of the
+//     coarse tile that contains the patch), and per batch of 8 obs stage into a ring of shared-memory stages:
+//     the 8 ye rows (cp.async), the pseudo-member column -innov/beta, omega[grid point][ob] = beta c1 GC(d),
+//     and the 8x8 Gram matrix (DMMA); batches are dealt round-robin to the 4 producer warps;
+//   * consumers only wait on the stage's `full` mbarrier, run  g = X Y^T -> 8-step recurrence -> X -= E Y, and
+//     arrive on its `empty` mbarrier.  No CTA-wide barrier after start-up.
+// Optionally fused with the mean/perturbation split and the recombination (assimilation.py:146-147, :168): with
+// xm == nullptr the kernel reads full ensemble values, forms mean and perturbations in registers and writes
+// mean + perturbation back, so the state crosses HBM exactly once (one read, one write of the touched rows).
+//
+// Candidate lists: a pre-pass (sweep_tile_*) builds, per coarse tile of 4x4 patches, the ascending list of obs
+// whose support cap can touch the tile; the producers' per-patch test then walks a few thousand entries instead
+// of every ob.  Without localisation (or when lists would not pay) the producers walk the ob range itself.
+#include "common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define SP_CW 12                      // consumer warps
+#define SP_PW 4                       // producer warps
+#define SP_NT ((SP_CW + SP_PW) * 32)
+#define SP_ROWS (SP_CW * 8)           // state rows per CTA
+#define SP_CT 4                       // coarse tile = SP_CT x SP_CT patches
+#define SP_MAXSTAGES 16
+
+struct SpParams {
+    double *xm;                       // nullptr: fused mean/perturbation split + recombination
+    double *Xp;
+    const double *Yp;
+    const double *grid_u;
+    const double *rec;
+    const double *geo;
+    const float4 *scan;               // (ux, uy, uz, theta) per ob; theta < 0: never a candidate
+    const int64_t *tile_off;          // candidate lists per coarse tile (nullptr: walk the ob range)
+    const int *tile_list;
+    unsigned long long *counters;
+    int64_t npts, nobs, ob_begin, ob_end;
+    int nlev, ny, nx, nens;
+    int y_begin, y_end;               // grid rows [y_begin, y_end) of the shard are swept by this launch
+    int pr0;                          // first patch row of this launch
+    int ty, tx, ntx, nctx;            // patch shape, patches along x, coarse tiles along x
+    int G, Lc, nlc;
+    int loc_mode;
+    int nstages, stage_doubles;       // ring geometry
+};
+
+__device__ __forceinline__ void sp_dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned sp_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(sp_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(sp_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = sp_smem(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <int NT3> __host__ __device__ constexpr int sp_yst() { return ((8 * NT3) % 16 == 8) ? 8 * NT3 : 8 * NT3 + 8; }
+
+// Stage layout (doubles): y[8][YST] | om[G][8] | Gram[64] | ob[6][8] | count (one double slot, int inside)
+template <int NT3> __host__ __device__ constexpr int sp_stage_doubles(int G) { return 8 * sp_yst<NT3>() + 8 * G + 64 + 48 + 2; }
+
+template <int NT3>
+__global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpParams p) {
+    constexpr int YST = sp_yst<NT3>();
+    constexpr int PC = 8 * NT3 - 1;          // column of the pseudo-member (the mean)
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_ring = reinterpret_cast<double *>(smem_raw);                                   // [nstages][stage_doubles]
+    double *s_gu = s_ring + (size_t)p.nstages * p.stage_doubles;                             // [3][SP_ROWS]
+    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_gu + 3 * SP_ROWS); // [SP_MAXSTAGES]
+    unsigned long long *s_empty = s_full + SP_MAXSTAGES;                                      // [SP_MAXSTAGES]
+    int *s_gvalid = reinterpret_cast<int *>(s_empty + SP_MAXSTAGES);                          // [SP_ROWS]
+    int *s_mine = s_gvalid + SP_ROWS;                                                         // [SP_PW][2][8]
+    __shared__ float s_bound[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 3, n = lane >> 2;
+    const int G = p.G, Lc = p.Lc, nens = p.nens;
+    const int S = p.nstages, SD = p.stage_doubles;
+
+    const int lc = blockIdx.x % p.nlc;
+    const int tile = blockIdx.x / p.nlc;
+    const int prow = p.pr0 + tile / p.ntx, pcol = tile % p.ntx;
+    const int y0 = prow * p.ty, x0 = pcol * p.tx;
+    const int l0 = lc * Lc;
+
+    // ---- start-up (the only CTA-wide barriers) ----------------------------------------------------
+    if (tid < G) {
+        const int gy = y0 + tid / p.tx, gx = x0 + tid % p.tx;
+        const bool ok = gy >= p.y_begin && gy < p.y_end && gx < p.nx;
+        const int cy = min(max(gy, p.y_begin), p.y_end - 1), cx = min(gx, p.nx - 1);
+        const int64_t pt = (int64_t)cy * p.nx + cx;
+        s_gu[tid] = p.grid_u[pt];
+        s_gu[SP_ROWS + tid] = p.grid_u[p.npts + pt];
+        s_gu[2 * SP_ROWS + tid] = p.grid_u[2 * p.npts + pt];
+        s_gvalid[tid] = ok;
+    }
+    for (int i = tid; i < S * SD; i += SP_NT) s_ring[i] = 0.0;           // padding columns stay zero for good
+    if (tid < S) {
+        sp_mbar_init(s_full + tid, 1);
+        sp_mbar_init(s_empty + tid, SP_CW);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double cx = 0, cy = 0, cz = 0;
+        for (int g = 0; g < G; ++g) { cx += s_gu[g]; cy += s_gu[SP_ROWS + g]; cz += s_gu[2 * SP_ROWS + g]; }
+        const double nn = sqrt(cx * cx + cy * cy + cz * cz);
+        if (nn > 1e-12) { cx /= nn; cy /= nn; cz /= nn; } else { cx = s_gu[0]; cy = s_gu[SP_ROWS]; cz = s_gu[2 * SP_ROWS]; }
+        double cmin = 1.0;
+        for (int g = 0; g < G; ++g) cmin = fmin(cmin, cx * s_gu[g] + cy * s_gu[SP_ROWS + g] + cz * s_gu[2 * SP_ROWS + g]);
+        s_bound[0] = (float)cx; s_bound[1] = (float)cy; s_bound[2] = (float)cz;
+        s_bound[3] = (float)(acos(fmax(-1.0, fmin(1.0, cmin))) + 1e-6);
+    }
+    __syncthreads();
+
+    if (warp >= SP_CW) {
+        // =============================== PRODUCER ===============================
+        const int pw = warp - SP_CW;
+        const float bcx = s_bound[0], bcy = s_bound[1], bcz = s_bound[2], brho = s_bound[3];
+        int *mine = s_mine + pw * 16;
+        unsigned long long npairs = 0;
+        const unsigned lt = (1u << lane) - 1u;
+
+        // stages batch b (nq valid obs, indices in cand[0..nq)); nq == 0 publishes the end marker
+        auto stage = [&](int b, int nq, const int *cand) {
+            const int s = b % S, u = b / S;
+            sp_mbar_wait(s_empty + s, (unsigned)((u & 1) ^ 1));
+            double *sy = s_ring + (size_t)s * SD;
+            double *som = sy + 8 * YST;
+            double *sG = som + 8 * G;
+            double *sob = sG + 64;
+            int *scnt = reinterpret_cast<int *>(sob + 48);
+            if (nq > 0) {
+                if (lane < 8) {
+                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, pc = 0;
+                    if (lane < nq) {
+                        const int64_t kk = cand[lane];
+                        v0 = p.geo[GEO_UX * p.nobs + kk]; v1 = p.geo[GEO_UY * p.nobs + kk]; v2 = p.geo[GEO_UZ * p.nobs + kk];
+                        v3 = p.geo[GEO_INVHW * p.nobs + kk]; v4 = p.geo[GEO_AMAX * p.nobs + kk];
+                        const double beta = p.rec[REC_BETA * p.nobs + kk];
+                        // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it below
+                        v5 = p.rec[REC_C1 * p.nobs + kk] * beta;
+                        pc = -p.rec[REC_INNOV * p.nobs + kk] / beta;
+                    }
+                    sob[0 * 8 + lane] = v0; sob[1 * 8 + lane] = v1; sob[2 * 8 + lane] = v2;
+                    sob[3 * 8 + lane] = v3; sob[4 * 8 + lane] = v4; sob[5 * 8 + lane] = v5;
+                    sy[lane * YST + (PC ^ (((lane >> 1) & 1) << 2))] = pc;
+                }
+#pragma unroll 1
+                for (int q = 0; q < 8; ++q) {
+                    double *dst = sy + q * YST;
+                    const int sw = ((q >> 1) & 1) << 2;
+                    if (q < nq) {
+                        const double *src = p.Yp + (int64_t)cand[q] * nens;
+                        if ((nens & 1) == 0) {
+                            for (int m = 2 * lane; m < nens; m += 64)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                        } else {
+                            for (int m = lane; m < nens; m += 32)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                        }
+                    } else {
+                        for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
+                    }
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+                __syncwarp();
+                // omega[g][q] = beta * loc / ((N-1) kdenom), one (ob, grid point) pair at a time per lane
+                for (int i = lane; i < 8 * G; i += 32) {
+                    const int q = i & 7, gg = i >> 3;
+                    double om = 0.0;
+                    if (q < nq && s_gvalid[gg]) {
+                        double w = 1.0;
+                        if (p.loc_mode == EXB_LOC_GC) {
+                            const double a = hav_a(s_gu[gg], s_gu[SP_ROWS + gg], s_gu[2 * SP_ROWS + gg],
+                                                   sob[0 * 8 + q], sob[1 * 8 + q], sob[2 * 8 + q]);
+                            w = loc_weight(a, sob[3 * 8 + q], sob[4 * 8 + q]);
+                        }
+                        if (w != 0.0 && lc == 0) npairs++;
+                        om = w * sob[5 * 8 + q];
+                    }
+                    som[i] = om;
+                }
+                asm volatile("cp.async.wait_all;\n" ::);
+                __syncwarp();
+                // Gram matrix of the batch (members only: the pseudo-member column is masked)
+                {
+                    double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+                    const double *yrow = sy + n * YST;
+                    const int sw = ((n >> 1) & 1) << 2;
+#pragma unroll
+                    for (int t = 0; t < NT3; ++t) {
+                        const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t + ((2 * c) ^ sw));
+                        const double v1 = (t == NT3 - 1 && c == 3) ? 0.0 : v.y;
+                        sp_dmma(g0, g1, v.x, v.x);
+                        sp_dmma(h0, h1, v1, v1);
+                    }
+                    sG[n * 8 + 2 * c] = g0 + h0;
+                    sG[n * 8 + 2 * c + 1] = g1 + h1;
+                }
+            }
+            if (lane == 0) *scnt = nq;
+            __syncwarp();
+            if (lane == 0) sp_mbar_arrive(s_full + s);
+        };
+
+        // walk the candidate source in serial order; batch b belongs to producer b % SP_PW
+        int64_t lb, le;
+        const int *list = nullptr;
+        if (p.tile_off) {
+            const int ct = (prow / SP_CT) * p.nctx + pcol / SP_CT;
+            lb = p.tile_off[ct];
+            le = p.tile_off[ct + 1];
+            list = p.tile_list;
+        } else {
+            lb = p.ob_begin;
+            le = p.ob_end;
+        }
+        int nseen = 0, bcur = pw;
+        for (int64_t base = lb; base < le; base += 32) {
+            const int64_t e = base + lane;
+            int idx = -1;
+            if (e < le) idx = list ? __ldg(list + e) : (int)e;
+            bool hit = false;
+            if (idx >= p.ob_begin && idx < p.ob_end) {
+                const float4 sc = __ldg(p.scan + idx);
+                if (sc.w >= 0.f) {
+                    const float ang = sc.w + brho;
+                    hit = (ang >= 3.1405f) || (sc.x * bcx + sc.y * bcy + sc.z * bcz >= __cosf(ang) - 4e-6f);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (!mask) continue;
+            if (hit) {
+                const int seq = nseen + __popc(mask & lt);
+                const int bb = seq >> 3;
+                if ((bb % SP_PW) == pw) mine[((bb / SP_PW) & 1) * 8 + (seq & 7)] = idx;
+            }
+            nseen += __popc(mask);
+            __syncwarp();
+            if (nseen >= 8 * (bcur + 1)) {
+                stage(bcur, 8, mine + ((bcur / SP_PW) & 1) * 8);
+                bcur += SP_PW;
+            }
+        }
+        const int total = (nseen + 7) >> 3;
+        if (bcur < total) {                                   // my last batch is the (partial) last one
+            stage(bcur, nseen - 8 * bcur, mine + ((bcur / SP_PW) & 1) * 8);
+            bcur += SP_PW;
+        }
+        if ((total % SP_PW) == pw) stage(total, 0, mine);     // end marker
+        if (p.counters) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+            if (lane == 0 && npairs) atomicAdd(&p.counters[1], npairs);
+        }
+        return;
+    }
+
+    // =============================== CONSUMER ===============================
+    const int r = warp * 8 + n;               // row slot in the CTA
+    const int g = r / Lc, l = r % Lc;
+    bool active = false;
+    int64_t row = 0;
+    if (g < G && l0 + l < p.nlev) {
+        const int gy = y0 + g / p.tx, gx = x0 + g % p.tx;
+        if (gy >= p.y_begin && gy < p.y_end && gx < p.nx) {
+            active = true;
+            row = (int64_t)(l0 + l) * p.npts + (int64_t)gy * p.nx + gx;
+        }
+    }
+    const int gslot = active ? g : 0;
+    const bool fused = p.xm == nullptr;
+    double x[2 * NT3];
+    {
+        double sum = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT3; ++t) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = 8 * t + 2 * c + h;
+                double v = 0.0;
+                if (active && m < nens) { v = p.Xp[row * nens + m]; sum += v; }
+                x[2 * t + h] = v;
+            }
+        }
+        if (fused) {
+            // ensemble mean and perturbations of the row (assimilation.py:146-147)
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const double mean = sum / (double)nens;
+#pragma unroll
+            for (int t = 0; t < NT3; ++t) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int m = 8 * t + 2 * c + h;
+                    if (m < nens) x[2 * t + h] -= mean;
+                }
+            }
+            if (c == 3) x[2 * NT3 - 1] = active ? mean : 0.0;
+        } else if (c == 3) {
+            x[2 * NT3 - 1] = active ? p.xm[row] : 0.0;      // the mean rides along in the last column
+        }
+    }
+    bool dirty = false;
+
+    for (int b = 0;; ++b) {
+        const int s = b % S, u = b / S;
+        sp_mbar_wait(s_full + s, (unsigned)(u & 1));
+        const double *sy = s_ring + (size_t)s * SD;
+        const double *som = sy + 8 * YST;
+        const double *Gb = som + 8 * G;
+        const int nq = *reinterpret_cast<const int *>(Gb + 64 + 48);
+        if (nq == 0) break;
+
+        // omega of this row's grid point for the 8 obs of the batch
+        double om[8];
+        {
+            const double2 *po = reinterpret_cast<const double2 *>(som + gslot * 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 v = po[i];
+                om[2 * i] = active ? v.x : 0.0;
+                om[2 * i + 1] = active ? v.y : 0.0;
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) any |= (om[i] != 0.0);
+        if (__any_sync(0xffffffffu, any)) {
+            // step 1: g[row][ob] = x[row] . y_ob  (two accumulator chains)
+            double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
+            {
+                const double *yrow = sy + n * YST;                // B operand: ob = n, members of lane c
+                const int sw = ((n >> 1) & 1) << 2;
+#pragma unroll
+                for (int t = 0; t < NT3; ++t) {
+                    const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t + ((2 * c) ^ sw));
+                    const double a1 = (t == NT3 - 1 && c == 3) ? 0.0 : x[2 * t + 1];   // mask the mean
+                    sp_dmma(ga0, ga1, x[2 * t], v.x);
+                    sp_dmma(gb0, gb1, a1, v.y);
+                }
+            }
+            ga0 += gb0;                                            // g[row][2c]
+            ga1 += gb1;                                            // g[row][2c+1]
+            // all-gather the 8 dots of the row over its 4 lanes
+            double gq[8];
+            {
+                const double o0 = __shfl_xor_sync(0xffffffffu, ga0, 1), o1 = __shfl_xor_sync(0xffffffffu, ga1, 1);
+                double q0, q1, q2, q3;
+                if (c & 1) { q0 = o0; q1 = o1; q2 = ga0; q3 = ga1; } else { q0 = ga0; q1 = ga1; q2 = o0; q3 = o1; }
+                const double r0 = __shfl_xor_sync(0xffffffffu, q0, 2), r1 = __shfl_xor_sync(0xffffffffu, q1, 2);
+                const double r2 = __shfl_xor_sync(0xffffffffu, q2, 2), r3 = __shfl_xor_sync(0xffffffffu, q3, 2);
+                if (c & 2) { gq[0] = r0; gq[1] = r1; gq[2] = r2; gq[3] = r3; gq[4] = q0; gq[5] = q1; gq[6] = q2; gq[7] = q3; }
+                else { gq[0] = q0; gq[1] = q1; gq[2] = q2; gq[3] = q3; gq[4] = r0; gq[5] = r1; gq[6] = r2; gq[7] = r3; }
+            }
+            // step 2: the serial recurrence inside the batch (per row; every lane of the row computes it)
+            double e[8];
+            e[0] = om[0] * gq[0];
+            e[1] = om[1] * (gq[1] - Gb[8] * e[0]);
+            e[2] = om[2] * (gq[2] - Gb[16] * e[0] - Gb[17] * e[1]);
+            e[3] = om[3] * (gq[3] - Gb[24] * e[0] - Gb[25] * e[1] - Gb[26] * e[2]);
+            {
+                // obs 4..7 see obs 0..3 through one more 8x8x4 product: corr[row][q] = sum_p e_p G[4+q][p]
+                const double ea = (c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3];
+                double k0 = 0.0, k1 = 0.0;
+                sp_dmma(k0, k1, ea, Gb[(4 + (n & 3)) * 8 + c]);
+                const double o0 = __shfl_xor_sync(0xffffffffu, k0, 1), o1 = __shfl_xor_sync(0xffffffffu, k1, 1);
+                if (c & 1) { gq[4] -= o0; gq[5] -= o1; gq[6] -= k0; gq[7] -= k1; }
+                else { gq[4] -= k0; gq[5] -= k1; gq[6] -= o0; gq[7] -= o1; }
+            }
+            e[4] = om[4] * gq[4];
+            e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
+            e[6] = om[6] * (gq[6] - Gb[52] * e[4] - Gb[53] * e[5]);
+            e[7] = om[7] * (gq[7] - Gb[60] * e[4] - Gb[61] * e[5] - Gb[62] * e[6]);
+
+            // step 3: x[row][:] -= sum_q e_q y_q[:]   (A = -e in two k-steps, B = y, C = x)
+            const double ea0 = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
+            const double ea1 = -((c == 0) ? e[4] : (c == 1) ? e[5] : (c == 2) ? e[6] : e[7]);
+            {
+                const int sw = ((c >> 1) & 1) << 2;                 // rows c and 4+c share this swizzle
+                const double *y0p = sy + c * YST + (n ^ sw);
+                const double *y1p = y0p + 4 * YST;
+#pragma unroll
+                for (int t = 0; t < NT3; ++t) {
+                    sp_dmma(x[2 * t], x[2 * t + 1], ea0, y0p[8 * t]);
+                    sp_dmma(x[2 * t], x[2 * t + 1], ea1, y1p[8 * t]);
+                }
+            }
+            dirty = true;
+        }
+        __syncwarp();
+        if (lane == 0) sp_mbar_arrive(s_empty + s);
+    }
+
+    // xam of the row (ensrf.py:130) lives in lane c = 3; every lane of the warp takes part in the shuffle
+    double mean = __shfl_sync(0xffffffffu, x[2 * NT3 - 1], (lane & ~3) | 3);
+    if (!fused) mean = 0.0;
+    if (active && dirty) {
+#pragma unroll
+        for (int t = 0; t < NT3; ++t) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = 8 * t + 2 * c + h;
+                if (m < nens) p.Xp[row * nens + m] = x[2 * t + h] + mean;               // assimilation.py:168 when fused
+                else if (m == PC && !fused) p.xm[row] = x[2 * t + h];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate lists per coarse tile
+// ------------------------------------------------------------------------------------------
+// bounding cap (centre, angular radius) of every coarse tile: one warp per tile
+__global__ void sweep_tile_caps_kernel(const double *__restrict__ grid_u, int64_t npts, int nx, int y_begin, int y_end, int pr0,
+                                       int cty, int ctx, int nctx, int ntiles, float4 *__restrict__ caps) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const int ya = max((pr0 / SP_CT + t / nctx) * cty, y_begin), yb = min((pr0 / SP_CT + t / nctx + 1) * cty, y_end);
+    const int xa = (t % nctx) * ctx, xb = min(xa + ctx, nx);
+    const int w = xb - xa, npt = max(yb - ya, 0) * w;
+    double cx = 0, cy = 0, cz = 0;
+    for (int i = lane; i < npt; i += 32) {
+        const int64_t pt = (int64_t)(ya + i / w) * nx + xa + i % w;
+        cx += grid_u[pt]; cy += grid_u[npts + pt]; cz += grid_u[2 * npts + pt];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o); cy += __shfl_xor_sync(0xffffffffu, cy, o); cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    const double nn = sqrt(cx * cx + cy * cy + cz * cz);
+    if (nn > 1e-9) { cx /= nn; cy /= nn; cz /= nn; }
+    double cmin = 1.0;
+    for (int i = lane; i < npt; i += 32) {
+        const int64_t pt = (int64_t)(ya + i / w) * nx + xa + i % w;
+        cmin = fmin(cmin, cx * grid_u[pt] + cy * grid_u[npts + pt] + cz * grid_u[2 * npts + pt]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+    if (lane == 0) {
+        // degenerate centre (tile wraps the globe): radius pi -> everything is a candidate
+        const double rho = (nn > 1e-9 && npt > 0) ? acos(fmax(-1.0, fmin(1.0, cmin))) + 1e-4 : 3.2;
+        caps[t] = make_float4((float)cx, (float)cy, (float)cz, (float)rho);
+    }
+}
+
+// FILL = false: cnt[t] = number of obs whose support can touch tile t; FILL = true: their ascending list
+template <bool FILL>
+__global__ void sweep_tile_list_kernel(const float4 *__restrict__ caps, int ntiles, const float4 *__restrict__ scan,
+                                       int64_t ob_begin, int64_t ob_end, int *__restrict__ cnt,
+                                       const int64_t *__restrict__ off, int *__restrict__ list) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const float4 cap = caps[t];
+    int64_t pos = FILL ? off[t] : 0;
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t base = ob_begin; base < ob_end; base += 32) {
+        const int64_t k = base + lane;
+        bool hit = false;
+        if (k < ob_end) {
+            const float4 sc = __ldg(scan + k);
+            if (sc.w >= 0.f) {
+                const float ang = sc.w + cap.w;
+                hit = (ang >= 3.1405f) || (sc.x * cap.x + sc.y * cap.y + sc.z * cap.z >= __cosf(ang) - 4e-6f);
+            }
+        }
+        if (FILL) {
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (hit) list[pos + __popc(b & lt)] = (int)k;
+            pos += __popc(b);
+        } else {
+            count += hit ? 1 : 0;
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if (lane == 0) cnt[t] = count;
+    }
+}
+
+// exclusive prefix sum of cnt[n] into off[n+1], n small (one CTA, serial over chunks of 1024)
+__global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict__ cnt, int n, int64_t *__restrict__ off) {
+    __shared__ long long part[1024];
+    __shared__ long long carry_s;
+    const int t = threadIdx.x;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int b = 0; b < n; b += 1024) {
+        const int i = b + t;
+        const long long v = i < n ? cnt[i] : 0;
+        part[t] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            const long long y = t >= d ? part[t - d] : 0;
+            __syncthreads();
+            part[t] += y;
+            __syncthreads();
+        }
+        const long long carry = carry_s;
+        if (i < n) off[i] = carry + part[t] - v;
+        __syncthreads();
+        if (t == 1023) carry_s = carry + part[1023];
+        __syncthreads();
+    }
+    if (t == 0) off[n] = carry_s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <int NT3>
+static int sp_launch(SpParams &p, cudaStream_t st) {
+    const int Lc = p.nlev < SP_ROWS ? p.nlev : SP_ROWS;
+    const int G = SP_ROWS / Lc;
+    int bty = 1, btx = G;
+    for (int ty = 1; ty * ty <= G; ++ty) {
+        const int tx = G / ty;
+        if (ty * tx > bty * btx || (ty * tx == bty * btx && ty > bty)) { bty = ty; btx = tx; }
+    }
+    if (btx > p.nx) btx = p.nx;
+    if (bty > p.ny) bty = p.ny;
+    p.ty = bty; p.tx = btx; p.G = bty * btx; p.Lc = Lc;
+    p.nlc = (p.nlev + Lc - 1) / Lc;
+    p.ntx = (p.nx + btx - 1) / btx;
+    p.pr0 = p.y_begin / bty;
+    const int pr1 = (p.y_end + bty - 1) / bty;              // patch rows [pr0, pr1)
+    const int nty = pr1 - p.pr0;
+    p.stage_doubles = sp_stage_doubles<NT3>(p.G);
+    int dev = 0, max_smem = 0;
+    EXB_CUDA(cudaGetDevice(&dev));
+    EXB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t fixed = sizeof(double) * 3 * SP_ROWS + sizeof(unsigned long long) * 2 * SP_MAXSTAGES +
+                         sizeof(int) * (SP_ROWS + SP_PW * 16) + 64;
+    int S = (int)(((size_t)max_smem - 1024 - fixed) / (sizeof(double) * p.stage_doubles));
+    if (S > 12) S = 12;
+    S -= S % SP_PW;                    // every use of a stage is staged by the same producer warp (parity waits)
+    if (S < 2 * SP_PW) return EXB_ERR_UNSUPPORTED;
+    p.nstages = S;
+    const size_t smem = fixed + sizeof(double) * (size_t)S * p.stage_doubles;
+    EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // candidate lists per coarse tile (localised runs only; the kernel walks the ob range otherwise)
+    float4 *caps = nullptr;
+    int *cnt = nullptr, *list = nullptr;
+    int64_t *off = nullptr;
+    p.tile_off = nullptr;
+    p.tile_list = nullptr;
+    const char *nolist = getenv("EXB_SWEEP_NOLIST");
+    if (p.loc_mode == EXB_LOC_GC && !(nolist && atoi(nolist)) && p.ob_end - p.ob_begin > 4096) {
+        const int cty = bty * SP_CT, ctx = btx * SP_CT;
+        p.nctx = (p.nx + ctx - 1) / ctx;
+        const int cr0 = p.pr0 / SP_CT, cr1 = (pr1 + SP_CT - 1) / SP_CT;
+        const int ntiles = (cr1 - cr0) * p.nctx;
+        EXB_CUDA(cudaMallocAsync(&caps, sizeof(float4) * ntiles, st));
+        EXB_CUDA(cudaMallocAsync(&cnt, sizeof(int) * ntiles, st));
+        EXB_CUDA(cudaMallocAsync(&off, sizeof(int64_t) * (ntiles + 1), st));
+        const unsigned gridw = (unsigned)ceil_div64((int64_t)ntiles * 32, 256);
+        sweep_tile_caps_kernel<<<gridw, 256, 0, st>>>(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, p.pr0, cty, ctx, p.nctx, ntiles, caps);
+        sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, cnt, nullptr, nullptr);
+        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off);
+        exb_count_launches(3);
+        long long total = 0;
+        EXB_CUDA(cudaMemcpyAsync(&total, off + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        EXB_CUDA(cudaStreamSynchronize(st));
+        EXB_CUDA(cudaMallocAsync(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
+        sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, nullptr, off, list);
+        exb_count_launches(1);
+        // the kernel indexes tiles by absolute coarse row: shift the offsets' base
+        p.tile_off = off - (int64_t)cr0 * p.nctx;
+        p.tile_list = list;
+    } else {
+        p.nctx = 1;
+    }
+    const int64_t nblocks = (int64_t)p.ntx * nty * p.nlc;
+    int rc = EXB_OK;
+    if (nblocks >= 0x7fffffff) {
+        exb_set_error("exb_state_sweep: too many patches for one launch");
+        rc = EXB_ERR_ARG;
+    } else if (nblocks > 0) {
+        state_sweep_pipe_kernel<NT3><<<(unsigned)nblocks, SP_NT, smem, st>>>(p);
+        exb_count_launches(1);
+        rc = exb_check_launch("state_sweep_pipe_kernel");
+    }
+    if (caps) { cudaFreeAsync(caps, st); cudaFreeAsync(cnt, st); cudaFreeAsync(off, st); cudaFreeAsync(list, st); }
+    return rc;
+}
+
+// Called from state_update.cu for float64 states.  xm == nullptr selects the fused split/recombine mode (Xp then
+// holds full ensemble values).  Returns EXB_ERR_UNSUPPORTED if no variant fits.
+int exb_state_sweep_pipe_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                             const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
+                             const float4 *scan, int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin,
+                             int64_t y_end, int loc_mode, unsigned long long *counters, cudaStream_t st) {
+    SpParams p;
+    p.xm = xm; p.Xp = Xp; p.Yp = Yp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
+    p.tile_off = nullptr; p.tile_list = nullptr;
+    p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;
+    p.nlev = (int)nlev; p.ny = (int)ny; p.nx = (int)nx; p.nens = nens; p.loc_mode = loc_mode;
+    p.y_begin = (int)y_begin; p.y_end = (int)y_end;
+    const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
+#define SP_TRY(N) if (need <= N) return sp_launch<N>(p, st)
+    SP_TRY(4);
+    SP_TRY(7);
+    SP_TRY(10);
+    SP_TRY(13);
+#undef SP_TRY
+    return EXB_ERR_UNSUPPORTED;                       // larger ensembles: state_update_mma.cu (fewer registers per row)
+}

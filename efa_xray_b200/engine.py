@@ -207,6 +207,25 @@ def state_update(xm, Xp, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, cou
               loc_mode, _lib.ptr(counters), _lib.stream_ptr())
 
 
+def state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, counters, y_begin=0, y_end=None,
+                      ob_begin=0, ob_end=None):
+    """Fused split + sweep + recombine of grid rows [y_begin, y_end) of a float64 shard holding full ensemble
+    values (exb_state_sweep_f64)."""
+    _lib.call('exb_state_sweep_f64', _lib.ptr(X), nlev, ny, nx, X.shape[-1], _lib.ptr(grid_u), _lib.ptr(Yp),
+              _lib.ptr(rec), _lib.ptr(geo), nobs, ob_begin, nobs if ob_end is None else ob_end, y_begin,
+              ny if y_end is None else y_end, loc_mode, _lib.ptr(counters), _lib.stream_ptr())
+
+
+def fused_sweep_available(dtype, nens):
+    """The fused kernel exists for float64 ensembles of up to 103 members; EXB_FUSED=0 or EXB_SU_IMPL=mma|vector
+    select the three-call form (split, sweep, recombine)."""
+    import os
+    torch = _torch()
+    if dtype != torch.float64 or nens > 103 or os.environ.get('EXB_FUSED', '1') == '0':
+        return False
+    return os.environ.get('EXB_SU_IMPL', 'pipe') == 'pipe'
+
+
 def upload_obs(obs: ObsArrays, device, loc_mode):
     torch = _torch()
     d = {
@@ -224,7 +243,7 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
 
 
 def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflation=None, timing=True,
-                    band=None, group=None, Y=None):
+                    band=None, group=None, Y=None, sweep_bands=None, on_band_done=None):
     """Serial EnSRF analysis of a device-resident ensemble, in place.
 
     X        torch tensor [nlev*ny*nx, nens] (float64 or float32) on a CUDA device, to_vect layout
@@ -232,6 +251,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
              only that latitude band, [nlev*(y1-y0)*nx, nens], of a state sharded over the ranks of `group`;
              `grid` always describes the full grid.
     inflation  None, or a numpy array of per-level multiplicative factors (length nlev).
+    sweep_bands  optional list of (ya, yb) row ranges of the shard: the fused sweep is issued range by range and
+             on_band_done(ya, yb) is called after each launch has been enqueued (e.g. to start its download).
     Returns an AnalysisResult with the per-ob diagnostics of ensrf.py:66-70,144-149 (identical on all ranks).
     """
     torch = _torch()
@@ -259,17 +280,26 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
         Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
         _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
-        xm = torch.empty(nrows, dtype=X.dtype, device=dev)
-        _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+        fused = fused_sweep_available(X.dtype, nens)
+        if not fused:
+            xm = torch.empty(nrows, dtype=X.dtype, device=dev)
+            _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
         tm.mark('setup')
         rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
         counters = torch.zeros(2, dtype=torch.int64, device=dev)
         obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx)
         tm.mark('obs_solve')
         grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
-        state_update(xm, X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
-        tm.mark('state_update')
-        _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+        if fused:
+            for ya, yb in (sweep_bands or [(0, ny)]):
+                state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb)
+                if on_band_done is not None:
+                    on_band_done(ya, yb)
+            tm.mark('state_update')
+        else:
+            state_update(xm, X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
+            tm.mark('state_update')
+            _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
         tm.mark('recombine')
         rec_h = rec.cpu().numpy()
         _lib.call('exb_obs_solve_async_status')
