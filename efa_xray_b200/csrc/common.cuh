@@ -79,6 +79,47 @@ __device__ __forceinline__ double loc_weight(double a, double inv_hw, double a_m
     return gaspari_cohn_r(r);
 }
 
+// ---- branch-free localisation weight for supports up to 5000 km -------------------------------------------
+// Same function as loc_weight, written without data-dependent branches or libm slow paths so that several
+// independent evaluations interleave in one thread (the libm asin/sqrt/division chain is latency-bound).
+// Valid for a_max <= EXB_FAST_AMAX (support angle <= 45.6 degrees, 5070 km); callers fall back to loc_weight
+// otherwise.  asin(sqrt(a)) = sqrt(a) * Q(a), Q(a) = sum_n c_n a^n, c_n = (2n)! / (4^n n!^2 (2n+1)); 20 terms
+// leave a remainder below 1e-19 at a = 0.15.  Reciprocal and reciprocal square root start from the fp32
+// special-function unit and take two Newton steps (relative error ~1e-28 before rounding).
+#define EXB_FAST_AMAX 0.15
+__device__ __forceinline__ double exb_asin_sqrt_over_sqrt(double a) {
+    // Horner on two interleaved halves (even/odd powers) to halve the dependent chain
+    const double a2 = a * a;
+    double pe = 0.0035692053938259347, po = 0.003297059503473485;   // c18, c19
+    pe = fma(pe, a2, 0.004240907093679363); po = fma(po, a2, 0.003880964558837669);   // c16, c17
+    pe = fma(pe, a2, 0.005153309682319905); po = fma(po, a2, 0.004660143486915096);   // c14, c15
+    pe = fma(pe, a2, 0.006447210311889649); po = fma(po, a2, 0.005740037670841924);   // c12, c13
+    pe = fma(pe, a2, 0.008390335809616815); po = fma(po, a2, 0.0073125258735988454);   // c10, c11
+    pe = fma(pe, a2, 0.011551800896139705); po = fma(po, a2, 0.009761609529194078);   // c8, c9
+    pe = fma(pe, a2, 0.017352764423076924); po = fma(po, a2, 0.01396484375);   // c6, c7
+    pe = fma(pe, a2, 0.030381944444444444); po = fma(po, a2, 0.022372159090909092);   // c4, c5
+    pe = fma(pe, a2, 0.075); po = fma(po, a2, 0.044642857142857144);   // c2, c3
+    pe = fma(pe, a2, 1.0); po = fma(po, a2, 0.16666666666666666);   // c0, c1
+    return fma(po, a, pe);
+}
+__device__ __forceinline__ double loc_weight_fast(double a, double inv_hw, double a_max) {
+    const bool inside = a < a_max;
+    a = fmin(fmax(a, 1e-30), EXB_FAST_AMAX);
+    double y = (double)rsqrtf((float)a);                       // 1/sqrt(a) to ~1e-7
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    const double s = a * y;                                    // sqrt(a)
+    const double r = (2.0 * EXB_R_EARTH) * inv_hw * s * exb_asin_sqrt_over_sqrt(a);
+    const double rc = fmin(fmax(r, 1.0), 2.0);
+    double ir = (double)__frcp_rn((float)rc);                  // 1/r on [1, 2]
+    ir = ir * fma(-rc, ir, 2.0);
+    ir = ir * fma(-rc, ir, 2.0);
+    const double p1 = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+    const double p2 = fma(fma(fma(fma(fma(r, 1.0 / 12.0, -0.5), r, 0.625), r, 5.0 / 3.0), r, -5.0), r, 4.0) - (2.0 / 3.0) * ir;
+    double w = (r <= 1.0) ? p1 : ((r < 2.0) ? p2 : 0.0);
+    return inside ? w : 0.0;
+}
+
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
 template <> struct Vec2<float> { typedef float2 type; };

@@ -63,7 +63,17 @@ __device__ __forceinline__ void sp_mbar_init(unsigned long long *bar, unsigned c
 __device__ __forceinline__ void sp_mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(sp_smem(bar)) : "memory");
 }
-__device__ __forceinline__ void sp_mbar_wait(unsigned long long *bar, unsigned parity) {
+// (two textually separate copies so that profiler samples of consumers waiting for data and of producers waiting
+// for a free stage land on different source lines)
+__device__ __forceinline__ void sp_mbar_wait_full(unsigned long long *bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = sp_smem(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void sp_mbar_wait_empty(unsigned long long *bar, unsigned parity) {
     unsigned ok = 0;
     const unsigned a = sp_smem(bar);
     do {
@@ -89,6 +99,7 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     unsigned long long *s_empty = s_full + SP_MAXSTAGES;                                      // [SP_MAXSTAGES]
     int *s_gvalid = reinterpret_cast<int *>(s_empty + SP_MAXSTAGES);                          // [SP_ROWS]
     int *s_mine = s_gvalid + SP_ROWS;                                                         // [SP_PW][2][8]
+    int *s_scanbuf = s_mine + SP_PW * 16;                                                     // [SP_PW][128]
     __shared__ float s_bound[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,10 +150,48 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
         unsigned long long npairs = 0;
         const unsigned lt = (1u << lane) - 1u;
 
-        // stages batch b (nq valid obs, indices in cand[0..nq)); nq == 0 publishes the end marker
-        auto stage = [&](int b, int nq, const int *cand) {
+        // A batch is staged in two halves so that two batches are in flight per producer warp and no global-memory
+        // latency is exposed: issue(b) waits for the stage to be free, starts the loads of the per-ob scalars (they
+        // stay in registers) and the cp.async copies of the 8 ye rows; finish(b) -- called after the NEXT batch of
+        // this warp has been issued -- writes the scalars, evaluates omega, waits for the rows, forms the Gram
+        // matrix and publishes the stage.  nq == 0 publishes the end marker.
+        struct Scal { double ux, uy, uz, ihw, amax, c1, beta, innov; };
+        auto issue = [&](int b, int nq, const int *cand, Scal &sc) {
             const int s = b % S, u = b / S;
-            sp_mbar_wait(s_empty + s, (unsigned)((u & 1) ^ 1));
+            sp_mbar_wait_empty(s_empty + s, (unsigned)((u & 1) ^ 1));
+            if (nq == 0) return;
+            double *sy = s_ring + (size_t)s * SD;
+            sc.ux = sc.uy = sc.uz = sc.ihw = sc.amax = sc.c1 = sc.innov = 0.0;
+            sc.beta = 1.0;
+            if (lane < nq) {
+                const int64_t kk = cand[lane];
+                sc.ux = __ldg(p.geo + GEO_UX * p.nobs + kk); sc.uy = __ldg(p.geo + GEO_UY * p.nobs + kk);
+                sc.uz = __ldg(p.geo + GEO_UZ * p.nobs + kk); sc.ihw = __ldg(p.geo + GEO_INVHW * p.nobs + kk);
+                sc.amax = __ldg(p.geo + GEO_AMAX * p.nobs + kk);
+                sc.c1 = __ldg(p.rec + REC_C1 * p.nobs + kk); sc.beta = __ldg(p.rec + REC_BETA * p.nobs + kk);
+                sc.innov = __ldg(p.rec + REC_INNOV * p.nobs + kk);
+            }
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+                double *dst = sy + q * YST;
+                const int sw = ((q >> 1) & 1) << 2;
+                if (q < nq) {
+                    const double *src = p.Yp + (int64_t)cand[q] * nens;
+                    if ((nens & 1) == 0) {
+                        for (int m = 2 * lane; m < nens; m += 64)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                    } else {
+                        for (int m = lane; m < nens; m += 32)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                    }
+                } else {
+                    for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        auto finish = [&](int b, int nq, const Scal &sc, bool newer_group_pending) {
+            const int s = b % S;
             double *sy = s_ring + (size_t)s * SD;
             double *som = sy + 8 * YST;
             double *sG = som + 8 * G;
@@ -150,56 +199,43 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             int *scnt = reinterpret_cast<int *>(sob + 48);
             if (nq > 0) {
                 if (lane < 8) {
-                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, pc = 0;
-                    if (lane < nq) {
-                        const int64_t kk = cand[lane];
-                        v0 = p.geo[GEO_UX * p.nobs + kk]; v1 = p.geo[GEO_UY * p.nobs + kk]; v2 = p.geo[GEO_UZ * p.nobs + kk];
-                        v3 = p.geo[GEO_INVHW * p.nobs + kk]; v4 = p.geo[GEO_AMAX * p.nobs + kk];
-                        const double beta = p.rec[REC_BETA * p.nobs + kk];
-                        // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it below
-                        v5 = p.rec[REC_C1 * p.nobs + kk] * beta;
-                        pc = -p.rec[REC_INNOV * p.nobs + kk] / beta;
-                    }
-                    sob[0 * 8 + lane] = v0; sob[1 * 8 + lane] = v1; sob[2 * 8 + lane] = v2;
-                    sob[3 * 8 + lane] = v3; sob[4 * 8 + lane] = v4; sob[5 * 8 + lane] = v5;
-                    sy[lane * YST + (PC ^ (((lane >> 1) & 1) << 2))] = pc;
+                    sob[0 * 8 + lane] = sc.ux; sob[1 * 8 + lane] = sc.uy; sob[2 * 8 + lane] = sc.uz;
+                    sob[3 * 8 + lane] = sc.ihw; sob[4 * 8 + lane] = sc.amax;
+                    // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it below
+                    sob[5 * 8 + lane] = sc.c1 * sc.beta;
+                    // pseudo-member column: the rank-8 update then also performs xam = xbm + kmat*innov (ensrf.py:130)
+                    sy[lane * YST + (PC ^ (((lane >> 1) & 1) << 2))] = (lane < nq) ? -sc.innov / sc.beta : 0.0;
                 }
-#pragma unroll 1
-                for (int q = 0; q < 8; ++q) {
-                    double *dst = sy + q * YST;
-                    const int sw = ((q >> 1) & 1) << 2;
-                    if (q < nq) {
-                        const double *src = p.Yp + (int64_t)cand[q] * nens;
-                        if ((nens & 1) == 0) {
-                            for (int m = 2 * lane; m < nens; m += 64)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
-                        } else {
-                            for (int m = lane; m < nens; m += 32)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
-                        }
-                    } else {
-                        for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
-                    }
-                }
-                asm volatile("cp.async.commit_group;\n" ::);
                 __syncwarp();
-                // omega[g][q] = beta * loc / ((N-1) kdenom), one (ob, grid point) pair at a time per lane
-                for (int i = lane; i < 8 * G; i += 32) {
-                    const int q = i & 7, gg = i >> 3;
-                    double om = 0.0;
-                    if (q < nq && s_gvalid[gg]) {
-                        double w = 1.0;
-                        if (p.loc_mode == EXB_LOC_GC) {
-                            const double a = hav_a(s_gu[gg], s_gu[SP_ROWS + gg], s_gu[2 * SP_ROWS + gg],
-                                                   sob[0 * 8 + q], sob[1 * 8 + q], sob[2 * 8 + q]);
-                            w = loc_weight(a, sob[3 * 8 + q], sob[4 * 8 + q]);
+                // supports of all 8 obs within the range of the branch-free weight function?
+                const bool fast = __all_sync(0xffffffffu, lane >= 8 || sc.amax <= EXB_FAST_AMAX);
+                // omega[g][q] = beta * loc / ((N-1) kdenom): lane-parallel over (grid point, ob) pairs, four
+                // independent evaluations in flight per lane
+                for (int i0 = lane; i0 < 8 * G; i0 += 128) {
+                    double omv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + 32 * j;
+                        const int q = i & 7, gg = min(i >> 3, G - 1);
+                        double w = 0.0;
+                        if (i < 8 * G && q < nq && s_gvalid[gg]) {
+                            w = 1.0;
+                            if (p.loc_mode == EXB_LOC_GC) {
+                                const double a = hav_a(s_gu[gg], s_gu[SP_ROWS + gg], s_gu[2 * SP_ROWS + gg],
+                                                       sob[0 * 8 + q], sob[1 * 8 + q], sob[2 * 8 + q]);
+                                w = fast ? loc_weight_fast(a, sob[3 * 8 + q], sob[4 * 8 + q])
+                                         : loc_weight(a, sob[3 * 8 + q], sob[4 * 8 + q]);
+                            }
+                            npairs += (w != 0.0 && lc == 0) ? 1 : 0;
                         }
-                        if (w != 0.0 && lc == 0) npairs++;
-                        om = w * sob[5 * 8 + q];
+                        omv[j] = w * sob[5 * 8 + q];
                     }
-                    som[i] = om;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + 32 * j < 8 * G) som[i0 + 32 * j] = omv[j];
                 }
-                asm volatile("cp.async.wait_all;\n" ::);
+                if (newer_group_pending) asm volatile("cp.async.wait_group 1;\n" ::);
+                else asm volatile("cp.async.wait_group 0;\n" ::);
                 __syncwarp();
                 // Gram matrix of the batch (members only: the pseudo-member column is masked)
                 {
@@ -235,38 +271,84 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             le = p.ob_end;
         }
         int nseen = 0, bcur = pw;
-        for (int64_t base = lb; base < le; base += 32) {
-            const int64_t e = base + lane;
-            int idx = -1;
-            if (e < le) idx = list ? __ldg(list + e) : (int)e;
-            bool hit = false;
-            if (idx >= p.ob_begin && idx < p.ob_end) {
-                const float4 sc = __ldg(p.scan + idx);
-                if (sc.w >= 0.f) {
-                    const float ang = sc.w + brho;
-                    hit = (ang >= 3.1405f) || (sc.x * bcx + sc.y * bcy + sc.z * bcz >= __cosf(ang) - 4e-6f);
+        int pend_b = -1, pend_nq = 0;             // batch issued but not finished
+        Scal pend_sc, new_sc;
+        int *sbuf = s_scanbuf + pw * 128;         // hits of the current group of 4 list chunks (ob index or -1)
+        // One loop, one call site of issue() and of finish() (they inline the localisation arithmetic; several
+        // copies would not fit the instruction cache next to the consumer loop).  Per iteration: either one chunk
+        // of 32 list entries is compacted, or one of the tail events happens.
+        int64_t base = lb;
+        int chunk = 4, tail = 0;
+        while (true) {
+            int emit_b = -1, emit_nq = 0;
+            bool do_issue = false;
+            if (base < le || chunk < 4) {
+                if (chunk == 4) {
+                    // next group of four chunks: their index loads and record gathers are in flight together
+                    int idx[4];
+                    float4 rec4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t e = base + 32 * j + lane;
+                        idx[j] = -1;
+                        if (e < le) idx[j] = list ? __ldg(list + e) : (int)e;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rec4[j] = make_float4(0.f, 0.f, 0.f, -1.f);
+                        if (idx[j] >= p.ob_begin && idx[j] < p.ob_end) rec4[j] = __ldg(p.scan + idx[j]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        bool hit = false;
+                        if (rec4[j].w >= 0.f) {
+                            const float ang = rec4[j].w + brho;
+                            hit = (ang >= 3.1405f) || (rec4[j].x * bcx + rec4[j].y * bcy + rec4[j].z * bcz >= __cosf(ang) - 4e-6f);
+                        }
+                        sbuf[32 * j + lane] = hit ? idx[j] : -1;
+                    }
+                    __syncwarp();
+                    base += 128;
+                    chunk = 0;
                 }
+                const int v = sbuf[32 * chunk + lane];
+                ++chunk;
+                const unsigned mask = __ballot_sync(0xffffffffu, v >= 0);
+                if (mask) {
+                    if (v >= 0) {
+                        const int seq = nseen + __popc(mask & lt);
+                        const int bb = seq >> 3;
+                        if ((bb % SP_PW) == pw) mine[((bb / SP_PW) & 1) * 8 + (seq & 7)] = v;
+                    }
+                    nseen += __popc(mask);
+                    __syncwarp();
+                    if (nseen >= 8 * (bcur + 1)) { emit_b = bcur; emit_nq = 8; do_issue = true; }
+                }
+            } else if (tail == 0) {
+                tail = 1;
+                if (bcur < ((nseen + 7) >> 3)) { emit_b = bcur; emit_nq = nseen - 8 * bcur; do_issue = true; }   // partial last batch
+            } else if (tail == 1) {
+                tail = 2;
+                const int total = (nseen + 7) >> 3;
+                if ((total % SP_PW) == pw) { emit_b = total; emit_nq = 0; do_issue = true; }                       // end marker
+            } else if (tail == 2) {
+                tail = 3;
+                emit_b = -2;                                                                                       // flush the pending batch
+            } else {
+                break;
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (!mask) continue;
-            if (hit) {
-                const int seq = nseen + __popc(mask & lt);
-                const int bb = seq >> 3;
-                if ((bb % SP_PW) == pw) mine[((bb / SP_PW) & 1) * 8 + (seq & 7)] = idx;
+            if (emit_b == -1) continue;
+            if (do_issue) {
+                issue(emit_b, emit_nq, mine + ((emit_b / SP_PW) & 1) * 8, new_sc);
+                if (emit_nq == 8) bcur += SP_PW;
+                else if (emit_nq > 0) bcur += SP_PW;
             }
-            nseen += __popc(mask);
-            __syncwarp();
-            if (nseen >= 8 * (bcur + 1)) {
-                stage(bcur, 8, mine + ((bcur / SP_PW) & 1) * 8);
-                bcur += SP_PW;
-            }
+            if (pend_b >= 0) finish(pend_b, pend_nq, pend_sc, do_issue && emit_nq > 0);
+            pend_b = do_issue ? emit_b : -1;
+            pend_nq = emit_nq;
+            pend_sc = new_sc;
         }
-        const int total = (nseen + 7) >> 3;
-        if (bcur < total) {                                   // my last batch is the (partial) last one
-            stage(bcur, nseen - 8 * bcur, mine + ((bcur / SP_PW) & 1) * 8);
-            bcur += SP_PW;
-        }
-        if ((total % SP_PW) == pw) stage(total, 0, mine);     // end marker
         if (p.counters) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
@@ -322,9 +404,10 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     }
     bool dirty = false;
 
-    for (int b = 0;; ++b) {
-        const int s = b % S, u = b / S;
-        sp_mbar_wait(s_full + s, (unsigned)(u & 1));
+    int s = 0;
+    unsigned par = 0;
+    for (;; s = (s + 1 == S) ? 0 : s + 1, par ^= (s == 0) ? 1u : 0u) {
+        sp_mbar_wait_full(s_full + s, par);
         const double *sy = s_ring + (size_t)s * SD;
         const double *som = sy + 8 * YST;
         const double *Gb = som + 8 * G;
@@ -342,9 +425,11 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                 om[2 * i + 1] = active ? v.y : 0.0;
             }
         }
-        bool any = false;
+        // any weight non-zero?  (integer test of the bit patterns: the FP64 pipe is the contended one)
+        long long anyb = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) any |= (om[i] != 0.0);
+        for (int i = 0; i < 8; ++i) anyb |= __double_as_longlong(om[i]);
+        const bool any = (anyb << 1) != 0;
         if (__any_sync(0xffffffffu, any)) {
             // step 1: g[row][ob] = x[row] . y_ob  (two accumulator chains)
             double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
@@ -551,9 +636,9 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t fixed = sizeof(double) * 3 * SP_ROWS + sizeof(unsigned long long) * 2 * SP_MAXSTAGES +
-                         sizeof(int) * (SP_ROWS + SP_PW * 16) + 64;
+                         sizeof(int) * (SP_ROWS + SP_PW * 16 + SP_PW * 128) + 64;
     int S = (int)(((size_t)max_smem - 1024 - fixed) / (sizeof(double) * p.stage_doubles));
-    if (S > 12) S = 12;
+    if (S > SP_MAXSTAGES) S = SP_MAXSTAGES;
     S -= S % SP_PW;                    // every use of a stage is staged by the same producer warp (parity waits)
     if (S < 2 * SP_PW) return EXB_ERR_UNSUPPORTED;
     p.nstages = S;

@@ -383,6 +383,8 @@ def test_sweep_variants_agree(kw):
         'pipe_bands': _analysis_with_env(case, {}, bands=[(0, 7), (7, 30), (30, ny - 1), (ny - 1, ny)]),
     }
     for name, (X, res) in runs.items():
-        assert res.state_pairs == res0.state_pairs, name
+        # pairs with a non-zero weight: identical up to the handful of pairs within rounding of the edge of a
+        # support (the branch-free weight function and the libm one may round a 1e-16 weight to 0 differently)
+        assert abs(res.state_pairs - res0.state_pairs) <= 1e-4 * res0.state_pairs, name
         np.testing.assert_allclose(X, ref, rtol=1e-11, err_msg=name)
         assert np.abs(X - ref).max() <= 1e-9 * inc, name
