@@ -338,7 +338,7 @@ def run_ours(args):
     # ---- e2e: host buffers, copies inside the timed region ------------------------------------
     e2e = None
     if not args.no_e2e:
-        Oh = torch.empty_like(Xh) if rank == 0 else None
+        Oh = torch.empty_like(Xh).pin_memory() if rank == 0 else None
         full = torch.empty((nrows, nens), dtype=tdtype, device=dev) if (rank == 0 and world > 1) else None
 
         def e2e_step():
@@ -360,9 +360,15 @@ def run_ours(args):
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         n_e2e = max(1, min(args.steps, 3))
+        e2e_walls = []
         for _ in range(n_e2e):
-            e2e_step()
+            t0 = time.perf_counter()
+            r = e2e_step()
+            torch.cuda.synchronize()
+            e2e_walls.append((round(1e3 * (time.perf_counter() - t0), 1), {k: round(v, 1) for k, v in r.ms.items()}))
         f1.record()
+        if os.environ.get('EXB_BENCH_DEBUG'):
+            print('e2e steps:', e2e_walls, file=sys.stderr)
         barrier()
         t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
         if world > 1:

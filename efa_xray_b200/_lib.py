@@ -65,6 +65,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.argtypes = argtypes
         fn.restype = _int
+    lib.exb_state_sweep_row_granularity.argtypes = [_i64, _i64, _i64]
+    lib.exb_state_sweep_row_granularity.restype = _int
     lib.exb_launch_count.argtypes = []
     lib.exb_launch_count.restype = C.c_int64
     lib.exb_last_error.argtypes = []

@@ -40,11 +40,12 @@ class EnSRF(Assimilation):
 
         if self.verbose: print("Computing observation priors")
         obs = self._obs_arrays(loc_mode)
-        host = np.ascontiguousarray(st.to_vect())
+        host = np.array(st.to_vect(), order='C', copy=True)     # the prior itself stays untouched (ensrf.py:165)
         tdtype = {'f64': torch.float64, 'f32': torch.float32}[self.dtype]
-        X = torch.from_numpy(host).to(dev).to(tdtype)
         if self.verbose: print("Beginning observation loop")
-        res = engine.analysis_device(X, nlev, st._grid_tables(), obs, loc_mode)
+        # host buffer in, analysis written back into it (upload, sweep and download overlap band by band)
+        res = engine.analysis_host(host, nlev, None, None, obs, loc_mode, device=dev, dtype=tdtype,
+                                   grid=st._grid_tables())
         self._check_exact(res.n_exact)
         self.last_result = res
 
@@ -64,5 +65,5 @@ class EnSRF(Assimilation):
 
         if self.verbose: print("Formatting posterior")
         post_state = deepcopy(self.prior)
-        post_state.from_vect(X.cpu().numpy().astype(host.dtype, copy=False))
+        post_state.from_vect(host)
         return post_state, self.obs

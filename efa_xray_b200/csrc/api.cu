@@ -40,12 +40,19 @@ extern "C" int exb_device_check(void) {
         cudaGetLastError();
         return EXB_ERR_NODEVICE;
     }
-    cudaDeviceProp prop;
-    EXB_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) {
-        exb_set_error("exb_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev,
-                      prop.major, prop.minor);
-        return EXB_ERR_NODEVICE;
+    // attribute queries, cached per device: cudaGetDeviceProperties takes tens of milliseconds while copies are
+    // in flight, and this check sits in front of every analysis
+    static int checked_major[64];
+    static bool checked[64];
+    if (dev < 0 || dev >= 64 || !checked[dev]) {
+        int major = 0, minor = 0;
+        EXB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        EXB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+        if (major != 10) {
+            exb_set_error("exb_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+            return EXB_ERR_NODEVICE;
+        }
+        if (dev >= 0 && dev < 64) { checked_major[dev] = major; checked[dev] = true; }
     }
     return EXB_OK;
 }

@@ -585,7 +585,8 @@ __global__ void sweep_tile_list_kernel(const float4 *__restrict__ caps, int ntil
 }
 
 // exclusive prefix sum of cnt[n] into off[n+1], n small (one CTA, serial over chunks of 1024)
-__global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict__ cnt, int n, int64_t *__restrict__ off) {
+__global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict__ cnt, int n, int64_t *__restrict__ off,
+                                                         long long *__restrict__ total_host) {
     __shared__ long long part[1024];
     __shared__ long long carry_s;
     const int t = threadIdx.x;
@@ -608,7 +609,10 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict_
         if (t == 1023) carry_s = carry + part[1023];
         __syncthreads();
     }
-    if (t == 0) off[n] = carry_s;
+    if (t == 0) {
+        off[n] = carry_s;
+        *total_host = carry_s;        // mapped pinned host word: no D2H copy queued behind band downloads
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -663,11 +667,15 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         const unsigned gridw = (unsigned)ceil_div64((int64_t)ntiles * 32, 256);
         sweep_tile_caps_kernel<<<gridw, 256, 0, st>>>(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, p.pr0, cty, ctx, p.nctx, ntiles, caps);
         sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, cnt, nullptr, nullptr);
-        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off);
+        static long long *total_host = nullptr, *total_dev = nullptr;
+        if (!total_host) {
+            EXB_CUDA(cudaHostAlloc(&total_host, sizeof(long long), cudaHostAllocMapped));
+            EXB_CUDA(cudaHostGetDevicePointer(&total_dev, total_host, 0));
+        }
+        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off, total_dev);
         exb_count_launches(3);
-        long long total = 0;
-        EXB_CUDA(cudaMemcpyAsync(&total, off + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, st));
         EXB_CUDA(cudaStreamSynchronize(st));
+        const long long total = *reinterpret_cast<volatile long long *>(total_host);
         EXB_CUDA(cudaMallocAsync(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
         sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, nullptr, off, list);
         exb_count_launches(1);
@@ -689,6 +697,21 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     }
     if (caps) { cudaFreeAsync(caps, st); cudaFreeAsync(cnt, st); cudaFreeAsync(off, st); cudaFreeAsync(list, st); }
     return rc;
+}
+
+// Row granularity of the patches for a state with nlev levels: sweeping row ranges whose edges are multiples of
+// this value never splits a patch between two calls.
+extern "C" int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx) {
+    const int Lc = nlev < SP_ROWS ? (int)nlev : SP_ROWS;
+    const int G = SP_ROWS / Lc;
+    int bty = 1, btx = G;
+    for (int ty = 1; ty * ty <= G; ++ty) {
+        const int tx = G / ty;
+        if (ty * tx > bty * btx || (ty * tx == bty * btx && ty > bty)) { bty = ty; btx = tx; }
+    }
+    if (btx > nx) btx = (int)nx;
+    if (bty > ny) bty = (int)ny;
+    return bty;
 }
 
 // Called from state_update.cu for float64 states.  xm == nullptr selects the fused split/recombine mode (Xp then

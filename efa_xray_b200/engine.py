@@ -139,10 +139,14 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False):
 def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, group=None):
     """Y[nobs, nens] = H X for all obs (compute_ob_priors, assimilation/assimilation.py:36-49).
 
+    X may also be a PINNED host tensor: the gather kernel then reads the <= 8 stencil rows per ob straight from
+    host memory over PCIe (unified addressing), which lets the obs-space solve start while the state is still
+    being uploaded.
+
     With band=(y0, y1), X holds only that latitude band of the state: each rank sums the stencil points it
     owns and the partial sums are all-reduced, so every rank ends with the same full Y."""
     torch = _torch()
-    dev = X.device
+    dev = grid.device
     idx4, w4, nex = stencil_search(grid, obs.lat, obs.lon)
     row0 = torch.as_tensor(obs.row0).to(dev)
     row1 = torch.as_tensor(obs.row1).to(dev)
@@ -243,7 +247,8 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
 
 
 def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflation=None, timing=True,
-                    band=None, group=None, Y=None, sweep_bands=None, on_band_done=None):
+                    band=None, group=None, Y=None, sweep_bands=None, on_band_done=None, before_band=None,
+                    obs_device=None):
     """Serial EnSRF analysis of a device-resident ensemble, in place.
 
     X        torch tensor [nlev*ny*nx, nens] (float64 or float32) on a CUDA device, to_vect layout
@@ -252,7 +257,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
              `grid` always describes the full grid.
     inflation  None, or a numpy array of per-level multiplicative factors (length nlev).
     sweep_bands  optional list of (ya, yb) row ranges of the shard: the fused sweep is issued range by range and
-             on_band_done(ya, yb) is called after each launch has been enqueued (e.g. to start its download).
+             on_band_done(ya, yb) is called after each launch has been enqueued (e.g. to start its download),
+             before_band(ya, yb) before it (e.g. to wait for its upload).
     Returns an AnalysisResult with the per-ob diagnostics of ensrf.py:66-70,144-149 (identical on all ranks).
     """
     torch = _torch()
@@ -273,9 +279,13 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             assert fac.shape == (nlev,)
             _lib.call('exb_inflate_' + sfx, _lib.ptr(X), nrows, nens, fac.ctypes.data_as(C.c_void_p), nlev,
                       ny * nx, _lib.stream_ptr())
-        obs_dev, geo = upload_obs(obs, dev, loc_mode)
+        # (small host-to-device copies: callers that stream the state in on another stream do them first and pass
+        # the result, or they would queue behind the state in the copy engine)
+        obs_dev, geo = obs_device if obs_device is not None else upload_obs(obs, dev, loc_mode)
         if Y is None:
             Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group)
+        elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
+            Yp, nex = Y
         else:       # ob priors H.x computed by the caller (e.g. before the state was scattered)
             Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
         Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
@@ -292,6 +302,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
         if fused:
             for ya, yb in (sweep_bands or [(0, ny)]):
+                if before_band is not None:
+                    before_band(ya, yb)
                 state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb)
                 if on_band_done is not None:
                     on_band_done(ya, yb)
@@ -310,11 +322,32 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                           obs_pairs=int(cnt[0]), ms=tm.result())
 
 
+def sweep_band_schedule(nlev, ny, nx, nbands=6):
+    """Row ranges for a band-by-band sweep whose bands are uploaded / downloaded while other bands are swept:
+    equal row counts (on a lat-lon grid every row has the same number of points, and with obs spread over the
+    sphere every point sees about the same number of obs), edges on patch-row boundaries, the last band halved
+    so that the download left exposed at the end is short.  The schedule only affects how well copies and
+    kernels overlap."""
+    g = max(1, int(_lib.load().exb_state_sweep_row_granularity(nlev, ny, nx)))
+    nbands = max(1, min(nbands, ny // g if ny >= g else 1))
+    edges = sorted(set([0, ny] + [int(round(ny * i / nbands / g)) * g for i in range(1, nbands)]))
+    edges = [e for e in edges if 0 <= e <= ny]
+    ya, yb = edges[-2], edges[-1]
+    mid = ((ya + yb) // 2 // g) * g
+    if ya < mid < yb:
+        edges.insert(-1, mid)
+    return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+
+
 def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflation=None, device='cuda:0',
-                  dtype=None, grid=None, out=None):
+                  dtype=None, grid=None, out=None, pipeline=True):
     """Host-buffer entry: X_host is a numpy array or CPU torch tensor [nlev*ny*nx, nens]; it is uploaded,
     analysed on `device`, and the analysis is written to `out` (default: back into X_host).  Pinned host
-    memory makes the copies asynchronous.  res.ms gains 'upload' and 'download'."""
+    memory makes the copies asynchronous.  With the fused float64 sweep (and pipeline=True) the state is swept
+    in latitude bands and each finished band is downloaded on a second stream while the next one is swept, so
+    only the last band's download is exposed; the upload is overlapped with the obs-space solve when X_host is
+    pinned (see ob_priors).  res.ms gains 'upload' (duration of the host-to-device copies) and 'download' (what is
+    left of the device-to-host copies after the last sweep)."""
     torch = _torch()
     _lib.require_device()
     Xh = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(X_host)
@@ -322,18 +355,73 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
     assert Xh.is_contiguous() and Oh.is_contiguous() and Oh.shape == Xh.shape
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     with torch.cuda.device(device):
-        ev[0].record()
-        X = Xh.to(device, non_blocking=True)
-        if dtype is not None and X.dtype != dtype:
-            X = X.to(dtype)
-        ev[1].record()
+        main = torch.cuda.current_stream()
         if grid is None:
             grid = GridTables(lat2d, lon2d, torch.device(device))
-        res = analysis_device(X, nlev, grid, obs, loc_mode, inflation)
-        ev[2].record()
-        Oh.copy_(X.to(Oh.dtype) if X.dtype != Oh.dtype else X, non_blocking=True)
-        ev[3].record()
-        torch.cuda.synchronize()
-        res.ms['upload'] = ev[0].elapsed_time(ev[1])
+        nens = Xh.shape[1]
+        xdtype = Xh.dtype if dtype is None else dtype
+        banded = (pipeline and fused_sweep_available(xdtype, nens) and Oh.dtype == xdtype and Xh.dtype == xdtype
+                  and loc_mode == LOC_GC and obs.nobs > 0)
+        if banded:
+            # Three streams: uploads (band by band, in sweep order), compute, downloads.  With a pinned source and
+            # no inflation step the ob priors are gathered straight from host memory, so the obs-space solve runs
+            # while the state is still arriving; a band is swept as soon as it is on the device and downloaded
+            # while the next ones are swept.
+            copy_in, copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+            npts = grid.ny * grid.nx
+            X = torch.empty((nlev * npts, nens), dtype=xdtype, device=device)
+            X3, H3, O3 = X.view(nlev, npts, nens), Xh.view(nlev, npts, nens), Oh.view(nlev, npts, nens)
+            bands = sweep_band_schedule(nlev, grid.ny, grid.nx)
+            ev[0].record()
+            obs_device = upload_obs(obs, torch.device(device), loc_mode)
+            Y = None
+            if inflation is None and Xh.is_pinned():
+                # PCIe is used by one thing at a time: first the gather (25 % of the state in 800-byte pieces),
+                # then the band uploads, which overlap the obs-space solve and the sweep of earlier bands
+                Y = ob_priors(Xh, grid, obs, _sfx(xdtype), nlev=nlev)
+            arrived = {}
+            copy_in.wait_stream(main)
+            with torch.cuda.stream(copy_in):
+                for ya, yb in bands:
+                    for lev in range(nlev):
+                        X3[lev, ya * grid.nx:yb * grid.nx].copy_(H3[lev, ya * grid.nx:yb * grid.nx], non_blocking=True)
+                    arrived[(ya, yb)] = torch.cuda.Event()
+                    arrived[(ya, yb)].record(copy_in)
+                up_done = torch.cuda.Event(enable_timing=True)
+                up_done.record(copy_in)
+            if Y is None:
+                main.wait_stream(copy_in)
+            ev[1].record()
+
+            def wait_upload(ya, yb):
+                main.wait_event(arrived[(ya, yb)])
+
+            def download(ya, yb):
+                done = torch.cuda.Event()
+                done.record(main)
+                copy_out.wait_event(done)
+                with torch.cuda.stream(copy_out):
+                    for lev in range(nlev):
+                        O3[lev, ya * grid.nx:yb * grid.nx].copy_(X3[lev, ya * grid.nx:yb * grid.nx], non_blocking=True)
+
+            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation, Y=Y, sweep_bands=bands,
+                                  before_band=wait_upload, on_band_done=download, obs_device=obs_device)
+            ev[2].record()
+            main.wait_stream(copy_out)
+            ev[3].record()
+            torch.cuda.synchronize()
+            res.ms['upload'] = ev[0].elapsed_time(up_done)
+        else:
+            ev[0].record()
+            X = Xh.to(device, non_blocking=True)
+            if dtype is not None and X.dtype != dtype:
+                X = X.to(dtype)
+            ev[1].record()
+            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation)
+            ev[2].record()
+            Oh.copy_(X.to(Oh.dtype) if X.dtype != Oh.dtype else X, non_blocking=True)
+            ev[3].record()
+            torch.cuda.synchronize()
+            res.ms['upload'] = ev[0].elapsed_time(ev[1])
         res.ms['download'] = ev[2].elapsed_time(ev[3])
     return res

@@ -177,6 +177,10 @@ int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nen
                         int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
                         void *stream);
 
+/* Number of grid rows per patch row of exb_state_sweep_f64 for this shape (a small positive integer, not a status
+ * code): row ranges whose edges are multiples of it are swept without splitting a patch between two calls. */
+int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx);
+
 /* ---- whole analysis with HOST buffers (one GPU) ------------------------------------------- */
 /* EnSRF(...).update() for callers that hold plain host arrays: uploads X, computes the ob priors,
  * runs the serial analysis, downloads the analysis ensemble.  fp64 throughout.

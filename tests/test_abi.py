@@ -23,7 +23,8 @@ def test_header_symbols_exported(lib):
 
 def test_binding_covers_header():
     from efa_xray_b200 import _lib
-    assert set(_declared()) == set(_lib.SIGNATURES) | {'exb_last_error', 'exb_launch_count'}
+    assert set(_declared()) == set(_lib.SIGNATURES) | {'exb_last_error', 'exb_launch_count',
+                                                        'exb_state_sweep_row_granularity'}
 
 
 def test_version_and_loud_failure_without_device(lib):
