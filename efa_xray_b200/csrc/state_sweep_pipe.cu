@@ -5,7 +5,8 @@
 // the FP64 tensor pipe busy only half of the time: every round of 64 candidates was scanned, staged and
 // weighted by the same warps that then issue the DMMAs, behind CTA-wide barriers.  Here
 //   * one CTA per SM = 12 CONSUMER warps (8 state rows each = 96 rows of one patch, in registers for the
-//     whole launch) + 4 PRODUCER warps;
+//     whole launch) + 4 PRODUCER warps; the producers are the warps of SM sub-partition 3, so that their scalar
+//     FP64 arithmetic does not queue behind the consumers' DMMAs (see the role mapping in the kernel);
 //   * producers find the patch's candidate obs in serial order (fp32 cap test over the candidate list of the
 //     coarse tile that contains the patch), and per batch of 8 obs stage into a ring of shared-memory stages:
 //     the 8 ye rows (cp.async), the pseudo-member column -innov/beta, omega[grid point][ob] = beta c1 GC(d),
@@ -50,6 +51,7 @@ struct SpParams {
     int G, Lc, nlc;
     int loc_mode;
     int nstages, stage_doubles;       // ring geometry
+    int role_split;
 };
 
 __device__ __forceinline__ void sp_dmma(double &c0, double &c1, double a, double b) {
@@ -142,9 +144,15 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     }
     __syncthreads();
 
-    if (warp >= SP_CW) {
+    // Roles by scheduler: warp w runs on SM sub-partition w % 4.  The FP64 tensor pipe and the scalar FP64 pipe
+    // share one issue port per sub-partition, arbitrated per instruction: a producer's 2-clock DFMA queued behind
+    // three consumers' 16-clock DMMAs costs ~20-50 clocks.  With p.role_split the producers own sub-partition 3
+    // (their localisation arithmetic then runs at the full scalar rate) and the consumers share the other three.
+    const bool is_producer = p.role_split ? ((warp & 3) == 3) : (warp >= SP_CW);
+    const int cw = p.role_split ? ((warp >> 2) * 3 + (warp & 3)) : warp;      // consumer index 0..11
+    if (is_producer) {
         // =============================== PRODUCER ===============================
-        const int pw = warp - SP_CW;
+        const int pw = p.role_split ? (warp >> 2) : (warp - SP_CW);
         const float bcx = s_bound[0], bcy = s_bound[1], bcz = s_bound[2], brho = s_bound[3];
         int *mine = s_mine + pw * 16;
         unsigned long long npairs = 0;
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     }
 
     // =============================== CONSUMER ===============================
-    const int r = warp * 8 + n;               // row slot in the CTA
+    const int r = cw * 8 + n;                 // row slot in the CTA
     const int g = r / Lc, l = r % Lc;
     bool active = false;
     int64_t row = 0;
@@ -726,6 +734,7 @@ int exb_state_sweep_pipe_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, i
     p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;
     p.nlev = (int)nlev; p.ny = (int)ny; p.nx = (int)nx; p.nens = nens; p.loc_mode = loc_mode;
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
+    p.role_split = getenv("EXB_SP_SPLIT") ? atoi(getenv("EXB_SP_SPLIT")) : 1;
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
 #define SP_TRY(N) if (need <= N) return sp_launch<N>(p, st)
     SP_TRY(4);

@@ -8,3 +8,4 @@ import json
 d=json.load(open('gpurun_out/e2e_bench.json'))
 print(d['ms_per_step'], d['step_ms'], d['phases_ms'], d['e2e'], d['gpu_launches'])
 PY
+timeout 300 python scratch/wait_probe.py 2>&1 | tail -2
