@@ -49,6 +49,17 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(args, cfg, world, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), when this
+    run is the configuration that capture was taken on; else None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    key = '%s/cutoff%.0f/%s/nobs%d/gpus%d' % (args.config, args.cutoff_km, args.dtype, cfg['nobs'], world)
+    with open(path) as f:
+        return json.load(f).get(key, {}).get(kernel)
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -295,12 +306,14 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         res = step()
-    peak_tf = None
+    peak_tf = peak_dmma = None
     if rank == 0:
         import ctypes as C
         tf = C.c_double(0.0)
         _lib.call('exb_measure_fp64_peak', C.byref(tf), _lib.stream_ptr())
         peak_tf = tf.value
+        _lib.call('exb_measure_dmma_peak', C.byref(tf), _lib.stream_ptr())
+        peak_dmma = tf.value
 
     sampler = ClockSampler(local_rank)
     barrier()
@@ -389,6 +402,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (state sweep) -----------------------------------------
     hbm_peak, peak_src = peaks()
     su_s = float(su_max.item()) * 1e-3
+    sweep_kernel = 'state_sweep_pipe_kernel' if (args.dtype == 'f64' and nens <= 103) else 'state_update_kernel'
     alg_bytes = state_pairs * 2.0 * (nens + 1) * esize          # |F_s| * 2 * (Nens+1) * sizeof(T)
     achieved = alg_bytes / su_s / 1e9 / world                   # per GPU
     flops = state_pairs * (4.0 * nens + 3.0)
@@ -402,15 +416,21 @@ def run_ours(args):
         'state_updates_per_s': state_pairs / (ms_step * 1e-3),
         'state_row_updates': state_pairs, 'obs_assimilated': nassim,
         'phases_ms': phases, 'step_ms': step_ms,
-        'roofline': {'bound': 'hbm', 'kernel': 'state_update_kernel', 'achieved': achieved, 'peak': hbm_peak,
-                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+        'roofline': {'bound': 'hbm', 'kernel': sweep_kernel, 'achieved': achieved, 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': measured_traffic(args, cfg, world, sweep_kernel),
+                     'peak_source': peak_src,
                      'note': 'achieved = ALGORITHMIC bytes of the per-observation formulation (sum_k |F_s(k)| * 2 * '
                              '(Nens+1) * sizeof(T)) / kernel time, per GPU.  The kernel is tile-stationary: the state '
-                             'crosses HBM once, so real DRAM traffic is far below the algorithmic bytes and frac > 1 '
-                             'is a traffic reduction; the binding limit is the FP64 pipe (roofline_fp64).'},
-        'roofline_fp64': {'bound': 'fp64_fma', 'achieved': flops / su_s / 1e12 / world, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                          'frac': (flops / su_s / 1e12 / world) / peak_tf if peak_tf else None,
-                          'peak_source': 'exb_measure_fp64_peak (dependent-free DFMA loop on all SMs, this run)'},
+                             'crosses HBM once, so real DRAM traffic (traffic, bytes per launch from ncu) is far below '
+                             'the algorithmic bytes and frac > 1 is a traffic reduction; the binding limit is the FP64 '
+                             'tensor pipe (roofline_fp64).'},
+        'roofline_fp64': {'bound': 'fp64_tensor', 'achieved': flops / su_s / 1e12 / world, 'peak': peak_dmma, 'unit': 'TFLOP/s',
+                          'frac': (flops / su_s / 1e12 / world) / peak_dmma if peak_dmma else None,
+                          'peak_fma': peak_tf, 'frac_of_fma_peak': (flops / su_s / 1e12 / world) / peak_tf if peak_tf else None,
+                          'peak_source': 'exb_measure_dmma_peak (mma.sync m8n8k4 f64, 8 independent tiles per warp) and '
+                                         'exb_measure_fp64_peak (DFMA loop), both in this run',
+                          'note': 'achieved = algorithmic flop (4 Nens + 3 per (row, ob) pair with non-zero weight) / '
+                                  'kernel time'},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
 
