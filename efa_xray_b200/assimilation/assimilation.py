@@ -175,3 +175,13 @@ def update(prior_state, obs, inflate=None, loc=False, nproc=1, verbose=False):
     not fork worker processes."""
     from .ensrf import EnSRF
     return EnSRF(prior_state, obs, nproc=nproc, inflation=inflate, verbose=verbose, loc=loc).update()
+
+
+def randomize_obs_order(obs, seed=None):
+    """Shuffle a list of observations in place and return it: the demo notebook assimilates in random order
+    (efa_demo.ipynb cell 11, lines 44-46).  With localisation the analysis depends on the serial order, so the
+    order used is part of the experiment; pass a seed to make it reproducible."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(len(obs))
+    obs[:] = [obs[i] for i in perm]
+    return obs
