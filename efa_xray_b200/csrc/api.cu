@@ -164,12 +164,28 @@ __global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *
     }
 }
 
+// Stream-ordered work buffers from the default memory pool, which is told to keep freed blocks (a 2.5 GB state
+// buffer costs ~100 ms to cudaMalloc/cudaFree on every call otherwise).
+int exb_pool_setup() {
+    static bool done = false;
+    if (done) return EXB_OK;
+    int dev = 0;
+    cudaMemPool_t pool;
+    EXB_CUDA(cudaGetDevice(&dev));
+    EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done = true;
+    return EXB_OK;
+}
+
 namespace {
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
     template <typename T> T *as() { return static_cast<T *>(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
 };
 }   // namespace
 
@@ -179,6 +195,18 @@ struct DevBuf {
         if (rc__ != EXB_OK) return rc__; \
     } while (0)
 
+extern "C" int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                                   const double *Yp, const double *rec, const double *obgeo, int64_t nobs,
+                                   int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode,
+                                   unsigned long long *counters, void *stream);
+extern "C" int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx);
+
+// Three streams: band uploads, compute, band downloads (see engine.analysis_host for the same pipeline in Python).
+//   pinned X_host, no inflation : the ob priors are gathered straight from host memory (unified addressing), then the
+//                                 bands are uploaded in sweep order while the obs-space solve runs; a band is swept
+//                                 as soon as it has arrived and downloaded while the next ones are swept
+//   otherwise                   : the state is uploaded first; the band-wise sweep / download overlap remains
+// Ensembles above 103 members (no fused sweep) use split -> sweep -> recombine on the whole state.
 extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int64_t nx, int nens,
                                   const double *lat_deg, const double *lon_deg, int64_t nobs,
                                   const double *ob_value, const double *ob_error, const double *ob_lat_deg,
@@ -189,59 +217,78 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     EXB_REQUIRE(X_host && lat_deg && lon_deg && ob_value && ob_error && ob_lat_deg && ob_lon_deg && ob_assimilate &&
                     ob_row0 && ob_row1 && ob_tw0 && ob_tw1 && ob_diag, "null pointer");
     EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nens >= 2 && nobs > 0, "bad sizes");
+    EXB_REQUIRE(loc_mode != EXB_LOC_GC || ob_halfwidth_km, "loc_mode GC needs halfwidths");
     EXB_TRY(exb_device_check());
+    EXB_TRY(exb_pool_setup());
     const int64_t npts = ny * nx, nrows = nlev * npts;
-    cudaStream_t st = nullptr;
-    EXB_CUDA(cudaStreamCreate(&st));
-    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sguard{st};
+    const size_t row_bytes = (size_t)nens * sizeof(double);
+    cudaStream_t st = nullptr, s_in = nullptr, s_out = nullptr;
+    EXB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    EXB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    EXB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t a, b, c; ~StreamGuard() { cudaStreamDestroy(a); cudaStreamDestroy(b); cudaStreamDestroy(c); } } sguard{st, s_in, s_out};
     cudaEvent_t ev[5];
     for (auto &e : ev) EXB_CUDA(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); } } eguard{ev};
 
-    DevBuf dX, dxm, dlat, dlon, dgu, dsl, dcl, dob, dassim, drow, dtw, dgeo, didx4, dw4, didx8, dw8, dY, dYm, drec, dcnt, dnex;
-    EXB_CUDA(dX.alloc((size_t)nrows * nens * sizeof(double)));
-    EXB_CUDA(dxm.alloc((size_t)nrows * sizeof(double)));
-    EXB_CUDA(dlat.alloc(npts * sizeof(double)));
-    EXB_CUDA(dlon.alloc(npts * sizeof(double)));
-    EXB_CUDA(dgu.alloc(3 * npts * sizeof(double)));
-    EXB_CUDA(dsl.alloc(npts * sizeof(double)));
-    EXB_CUDA(dcl.alloc(npts * sizeof(double)));
-    EXB_CUDA(dob.alloc(7 * nobs * sizeof(double)));      // value error lat lon hw sinlat coslon
-    EXB_CUDA(dassim.alloc(nobs));
-    EXB_CUDA(drow.alloc(2 * nobs * sizeof(int64_t)));
-    EXB_CUDA(dtw.alloc(2 * nobs * sizeof(double)));
-    EXB_CUDA(dgeo.alloc(EXB_GEO_FIELDS * nobs * sizeof(double)));
-    EXB_CUDA(didx4.alloc(4 * nobs * sizeof(int64_t)));
-    EXB_CUDA(dw4.alloc(4 * nobs * sizeof(double)));
-    EXB_CUDA(didx8.alloc(8 * nobs * sizeof(int64_t)));
-    EXB_CUDA(dw8.alloc(8 * nobs * sizeof(double)));
-    EXB_CUDA(dY.alloc((size_t)nobs * nens * sizeof(double)));
-    EXB_CUDA(dYm.alloc(nobs * sizeof(double)));
-    EXB_CUDA(drec.alloc(EXB_REC_FIELDS * nobs * sizeof(double)));
-    EXB_CUDA(dcnt.alloc(2 * sizeof(unsigned long long)));
-    EXB_CUDA(dnex.alloc(sizeof(int32_t)));
+    DevBuf dX, dxm, dlat, dlon, dlaty, dlonx, dgu, dsl, dcl, dob, dassim, drow, dtw, dgeo, didx4, dw4, didx8, dw8, dY, dYm, drec, dcnt, dnex;
+    EXB_CUDA(dX.alloc((size_t)nrows * row_bytes, st));
+    EXB_CUDA(dlat.alloc(npts * sizeof(double), st));
+    EXB_CUDA(dlon.alloc(npts * sizeof(double), st));
+    EXB_CUDA(dgu.alloc(3 * npts * sizeof(double), st));
+    EXB_CUDA(dsl.alloc(npts * sizeof(double), st));
+    EXB_CUDA(dcl.alloc(npts * sizeof(double), st));
+    EXB_CUDA(dob.alloc(7 * nobs * sizeof(double), st));      // value error lat lon hw sinlat coslon
+    EXB_CUDA(dassim.alloc(nobs, st));
+    EXB_CUDA(drow.alloc(2 * nobs * sizeof(int64_t), st));
+    EXB_CUDA(dtw.alloc(2 * nobs * sizeof(double), st));
+    EXB_CUDA(dgeo.alloc(EXB_GEO_FIELDS * nobs * sizeof(double), st));
+    EXB_CUDA(didx4.alloc(4 * nobs * sizeof(int64_t), st));
+    EXB_CUDA(dw4.alloc(4 * nobs * sizeof(double), st));
+    EXB_CUDA(didx8.alloc(8 * nobs * sizeof(int64_t), st));
+    EXB_CUDA(dw8.alloc(8 * nobs * sizeof(double), st));
+    EXB_CUDA(dY.alloc((size_t)nobs * row_bytes, st));
+    EXB_CUDA(dYm.alloc(nobs * sizeof(double), st));
+    EXB_CUDA(drec.alloc(EXB_REC_FIELDS * nobs * sizeof(double), st));
+    EXB_CUDA(dcnt.alloc(8 * sizeof(unsigned long long), st));
+    EXB_CUDA(dnex.alloc(sizeof(int32_t), st));
 
-    // host-side tables of the pseudo-metric (state/ensemble.py:160-163)
-    std::vector<double> sl(npts), cl(npts), osl(nobs), ocl(nobs);
-    for (int64_t i = 0; i < npts; ++i) { sl[i] = sin(lat_deg[i] * EXB_DEG2RAD); cl[i] = cos(lon_deg[i] * EXB_DEG2RAD); }
+    // host-side tables of the pseudo-metric (state/ensemble.py:160-163).  Rectilinear grids (lat a function of y,
+    // lon a function of x: every regular lat-lon grid) take the separable O(ny+nx) search.
+    bool rect = true;
+    for (int64_t y = 0; y < ny && rect; ++y)
+        for (int64_t x = 0; x < nx; ++x)
+            if (lat_deg[y * nx + x] != lat_deg[y * nx] || lon_deg[y * nx + x] != lon_deg[x]) { rect = false; break; }
+    const int64_t ntab = rect ? (ny > nx ? ny : nx) : npts;
+    std::vector<double> sl(ntab), cl(ntab), osl(nobs), ocl(nobs), laty, lonx;
+    if (rect) {
+        laty.resize(ny); lonx.resize(nx);
+        for (int64_t y = 0; y < ny; ++y) { laty[y] = lat_deg[y * nx]; sl[y] = sin(laty[y] * EXB_DEG2RAD); }
+        for (int64_t x = 0; x < nx; ++x) { lonx[x] = lon_deg[x]; cl[x] = cos(lonx[x] * EXB_DEG2RAD); }
+    } else {
+        for (int64_t i = 0; i < npts; ++i) { sl[i] = sin(lat_deg[i] * EXB_DEG2RAD); cl[i] = cos(lon_deg[i] * EXB_DEG2RAD); }
+    }
     for (int64_t k = 0; k < nobs; ++k) { osl[k] = sin(ob_lat_deg[k] * EXB_DEG2RAD); ocl[k] = cos(ob_lon_deg[k] * EXB_DEG2RAD); }
 
+    // ---- small uploads first: nothing small may queue behind the state in the copy engine -------------------
     double *ob = dob.as<double>();
     EXB_CUDA(cudaEventRecord(ev[0], st));
-    EXB_CUDA(cudaMemcpyAsync(dX.p, X_host, (size_t)nrows * nens * sizeof(double), cudaMemcpyHostToDevice, st));
-    EXB_CUDA(cudaEventRecord(ev[1], st));
     EXB_CUDA(cudaMemcpyAsync(dlat.p, lat_deg, npts * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(dlon.p, lon_deg, npts * sizeof(double), cudaMemcpyHostToDevice, st));
-    EXB_CUDA(cudaMemcpyAsync(dsl.p, sl.data(), npts * sizeof(double), cudaMemcpyHostToDevice, st));
-    EXB_CUDA(cudaMemcpyAsync(dcl.p, cl.data(), npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dsl.p, sl.data(), (rect ? ny : npts) * sizeof(double), cudaMemcpyHostToDevice, st));
+    EXB_CUDA(cudaMemcpyAsync(dcl.p, cl.data(), (rect ? nx : npts) * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (rect) {
+        EXB_CUDA(dlaty.alloc(ny * sizeof(double), st));
+        EXB_CUDA(dlonx.alloc(nx * sizeof(double), st));
+        EXB_CUDA(cudaMemcpyAsync(dlaty.p, laty.data(), ny * sizeof(double), cudaMemcpyHostToDevice, st));
+        EXB_CUDA(cudaMemcpyAsync(dlonx.p, lonx.data(), nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     EXB_CUDA(cudaMemcpyAsync(ob + 0 * nobs, ob_value, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(ob + 1 * nobs, ob_error, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(ob + 2 * nobs, ob_lat_deg, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(ob + 3 * nobs, ob_lon_deg, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (loc_mode == EXB_LOC_GC) {
-        EXB_REQUIRE(ob_halfwidth_km, "loc_mode GC needs halfwidths");
+    if (loc_mode == EXB_LOC_GC)
         EXB_CUDA(cudaMemcpyAsync(ob + 4 * nobs, ob_halfwidth_km, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
     EXB_CUDA(cudaMemcpyAsync(ob + 5 * nobs, osl.data(), nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(ob + 6 * nobs, ocl.data(), nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(dassim.p, ob_assimilate, nobs, cudaMemcpyHostToDevice, st));
@@ -249,54 +296,147 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     EXB_CUDA(cudaMemcpyAsync(drow.as<int64_t>() + nobs, ob_row1, nobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(dtw.p, ob_tw0, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
     EXB_CUDA(cudaMemcpyAsync(dtw.as<double>() + nobs, ob_tw1, nobs * sizeof(double), cudaMemcpyHostToDevice, st));
-    EXB_CUDA(cudaMemsetAsync(dcnt.p, 0, 2 * sizeof(unsigned long long), st));
-
-    // setup: inflation, geometry, forward operator, mean/perturbation split
-    if (inflation != 1.0) EXB_TRY(exb_inflate_f64(dX.as<double>(), nrows, nens, &inflation, 1, nrows, st));
+    EXB_CUDA(cudaMemsetAsync(dcnt.p, 0, 8 * sizeof(unsigned long long), st));
     EXB_TRY(exb_grid_unitvec(dlat.as<double>(), dlon.as<double>(), npts, dgu.as<double>(), st));
     EXB_TRY(exb_obs_prepare(ob + 2 * nobs, ob + 3 * nobs, ob + 4 * nobs, nobs, loc_mode, dgeo.as<double>(), st));
-    EXB_TRY(exb_stencil_search(dsl.as<double>(), dcl.as<double>(), dlat.as<double>(), dlon.as<double>(), npts,
-                               ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs, didx4.as<int64_t>(),
-                               dw4.as<double>(), dnex.as<int32_t>(), st));
+    if (rect)
+        EXB_TRY(exb_stencil_search_rect(dsl.as<double>(), dcl.as<double>(), dlaty.as<double>(), dlonx.as<double>(), ny, nx,
+                                        ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs,
+                                        didx4.as<int64_t>(), dw4.as<double>(), dnex.as<int32_t>(), st));
+    else
+        EXB_TRY(exb_stencil_search(dsl.as<double>(), dcl.as<double>(), dlat.as<double>(), dlon.as<double>(), npts,
+                                   ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs, didx4.as<int64_t>(),
+                                   dw4.as<double>(), dnex.as<int32_t>(), st));
     stencil8_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(didx4.as<int64_t>(), dw4.as<double>(),
                                                                      drow.as<int64_t>(), drow.as<int64_t>() + nobs,
                                                                      dtw.as<double>(), dtw.as<double>() + nobs, nobs,
                                                                      didx8.as<int64_t>(), dw8.as<double>());
     exb_count_launches(1);
     EXB_TRY(exb_check_launch("stencil8_kernel"));
-    EXB_TRY(exb_gather_f64(dX.as<double>(), nrows, nens, didx8.as<int64_t>(), dw8.as<double>(), 8, nobs,
-                           dY.as<double>(), st));
+
+    // ---- band schedule ----------------------------------------------------------------------------------
+    const bool fused = nens <= 103;
+    std::vector<int64_t> edges;
+    if (fused) {
+        const int64_t g = exb_state_sweep_row_granularity(nlev, ny, nx);
+        int64_t nb = 6;
+        if (nb > ny / g) nb = ny / g > 0 ? ny / g : 1;
+        edges.push_back(0);
+        for (int64_t i = 1; i < nb; ++i) {
+            const int64_t e = (int64_t)llround((double)ny * i / nb / g) * g;
+            if (e > edges.back() && e < ny) edges.push_back(e);
+        }
+        const int64_t mid = ((edges.back() + ny) / 2 / g) * g;        // halve the last band: short exposed download
+        if (mid > edges.back() && mid < ny) edges.push_back(mid);
+        edges.push_back(ny);
+    } else {
+        edges = {0, ny};
+    }
+    const size_t nbands = edges.size() - 1;
+    std::vector<cudaEvent_t> arrived(nbands), swept(nbands);
+    for (size_t b = 0; b < nbands; ++b) {
+        EXB_CUDA(cudaEventCreateWithFlags(&arrived[b], cudaEventDisableTiming));
+        EXB_CUDA(cudaEventCreateWithFlags(&swept[b], cudaEventDisableTiming));
+    }
+    struct BandEvGuard { std::vector<cudaEvent_t> &a, &b; ~BandEvGuard() { for (auto e : a) cudaEventDestroy(e); for (auto e : b) cudaEventDestroy(e); } } bguard{arrived, swept};
+    auto band_copy = [&](size_t b, bool to_device, cudaStream_t s) -> cudaError_t {
+        for (int64_t lev = 0; lev < nlev; ++lev) {
+            const size_t off = ((size_t)lev * npts + (size_t)edges[b] * nx) * nens;
+            const size_t bytes = (size_t)(edges[b + 1] - edges[b]) * nx * row_bytes;
+            cudaError_t e = to_device ? cudaMemcpyAsync(dX.as<double>() + off, X_host + off, bytes, cudaMemcpyHostToDevice, s)
+                                      : cudaMemcpyAsync(X_host + off, dX.as<double>() + off, bytes, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+
+    // ---- ob priors and state upload -------------------------------------------------------------------------
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    const double *X_zero_copy = nullptr;
+    if (cudaPointerGetAttributes(&attr, X_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+        pinned = true;
+        X_zero_copy = static_cast<const double *>(attr.devicePointer);
+    }
+    cudaGetLastError();
+    const bool early_gather = pinned && inflation == 1.0;
+    if (early_gather) {
+        // PCIe carries one thing at a time: first the gather (<= 8 rows per ob), then the bands
+        EXB_TRY(exb_gather_f64(X_zero_copy, nrows, nens, didx8.as<int64_t>(), dw8.as<double>(), 8, nobs, dY.as<double>(), st));
+        EXB_CUDA(cudaEventRecord(ev[1], st));
+        EXB_CUDA(cudaStreamWaitEvent(s_in, ev[1], 0));
+    } else {
+        EXB_CUDA(cudaEventRecord(ev[1], st));
+        EXB_CUDA(cudaStreamWaitEvent(s_in, ev[1], 0));
+    }
+    for (size_t b = 0; b < nbands; ++b) {
+        EXB_CUDA(band_copy(b, true, s_in));
+        EXB_CUDA(cudaEventRecord(arrived[b], s_in));
+    }
+    if (!early_gather) {
+        EXB_CUDA(cudaStreamWaitEvent(st, arrived[nbands - 1], 0));
+        if (inflation != 1.0) EXB_TRY(exb_inflate_f64(dX.as<double>(), nrows, nens, &inflation, 1, nrows, st));
+        EXB_TRY(exb_gather_f64(dX.as<double>(), nrows, nens, didx8.as<int64_t>(), dw8.as<double>(), 8, nobs, dY.as<double>(), st));
+    }
     EXB_TRY(exb_split_mean_pert_f64(dY.as<double>(), dYm.as<double>(), nobs, nens, st));
-    EXB_TRY(exb_split_mean_pert_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
     EXB_CUDA(cudaEventRecord(ev[2], st));
 
-    // the serial analysis
+    // ---- the serial analysis: obs-space solve, then the state band by band ----------------------------------
     EXB_TRY(exb_obs_solve_f64(dYm.as<double>(), dY.as<double>(), ob + 0 * nobs, ob + 1 * nobs, dassim.as<uint8_t>(),
                               dgeo.as<double>(), nobs, nens, loc_mode, drec.as<double>(),
                               dcnt.as<unsigned long long>(), st));
-    EXB_TRY(exb_state_update_f64(dxm.as<double>(), dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(),
-                                 dY.as<double>(), drec.as<double>(), dgeo.as<double>(), nobs, 0, nobs, loc_mode,
-                                 dcnt.as<unsigned long long>(), st));
-    EXB_TRY(exb_recombine_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
-    EXB_CUDA(cudaEventRecord(ev[3], st));
-
-    EXB_CUDA(cudaMemcpyAsync(X_host, dX.p, (size_t)nrows * nens * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (fused) {
+        for (size_t b = 0; b < nbands; ++b) {
+            EXB_CUDA(cudaStreamWaitEvent(st, arrived[b], 0));
+            EXB_TRY(exb_state_sweep_f64(dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(), dY.as<double>(), drec.as<double>(),
+                                        dgeo.as<double>(), nobs, 0, nobs, edges[b], edges[b + 1], loc_mode,
+                                        dcnt.as<unsigned long long>(), st));
+            EXB_CUDA(cudaEventRecord(swept[b], st));
+            // download of the band that finished before this one (pageable destinations block the host here while
+            // this band is being swept, pinned ones do not block at all)
+            if (b > 0) {
+                EXB_CUDA(cudaStreamWaitEvent(s_out, swept[b - 1], 0));
+                EXB_CUDA(band_copy(b - 1, false, s_out));
+            }
+        }
+        EXB_CUDA(cudaEventRecord(ev[3], st));
+        EXB_CUDA(cudaStreamWaitEvent(s_out, swept[nbands - 1], 0));
+        EXB_CUDA(band_copy(nbands - 1, false, s_out));
+    } else {
+        EXB_CUDA(dxm.alloc((size_t)nrows * sizeof(double), st));
+        EXB_CUDA(cudaStreamWaitEvent(st, arrived[nbands - 1], 0));
+        EXB_TRY(exb_split_mean_pert_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
+        EXB_TRY(exb_state_update_f64(dxm.as<double>(), dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(),
+                                     dY.as<double>(), drec.as<double>(), dgeo.as<double>(), nobs, 0, nobs, loc_mode,
+                                     dcnt.as<unsigned long long>(), st));
+        EXB_TRY(exb_recombine_f64(dX.as<double>(), dxm.as<double>(), nrows, nens, st));
+        EXB_CUDA(cudaEventRecord(ev[3], st));
+        EXB_CUDA(cudaEventRecord(swept[0], st));
+        EXB_CUDA(cudaStreamWaitEvent(s_out, swept[0], 0));
+        EXB_CUDA(band_copy(0, false, s_out));
+    }
+    EXB_CUDA(cudaEventRecord(ev[4], s_out));
+    EXB_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
     EXB_CUDA(cudaMemcpyAsync(ob_diag, drec.p, 4 * nobs * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EXB_CUDA(cudaEventRecord(ev[4], st));
     unsigned long long cnt[2] = {0, 0};
     int32_t nex = 0;
     EXB_CUDA(cudaMemcpyAsync(cnt, dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
     EXB_CUDA(cudaMemcpyAsync(&nex, dnex.p, sizeof(nex), cudaMemcpyDeviceToHost, st));
     EXB_CUDA(cudaStreamSynchronize(st));
+    EXB_CUDA(cudaStreamSynchronize(s_in));
+    EXB_CUDA(cudaStreamSynchronize(s_out));
     EXB_TRY(exb_obs_solve_async_status());
     if (stats) {
-        float ms[4];
-        for (int i = 0; i < 4; ++i) EXB_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        float ms[4] = {0.f, 0.f, 0.f, 0.f};
+        EXB_CUDA(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));      // small uploads + stencils (+ zero-copy gather)
+        EXB_CUDA(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));      // state upload wait / ob-prior split
+        EXB_CUDA(cudaEventElapsedTime(&ms[2], ev[2], ev[3]));      // obs-space solve + sweeps (uploads/downloads overlapped)
+        EXB_CUDA(cudaEventElapsedTime(&ms[3], ev[3], ev[4]));      // download left exposed after the last sweep
         stats[0] = (double)cnt[1] * (double)nlev;
         stats[1] = (double)cnt[0];
         stats[2] = (double)nex;
         for (int i = 0; i < 4; ++i) stats[3 + i] = ms[i];
-        stats[7] = 0.0;
+        stats[7] = (double)nbands;
     }
     return EXB_OK;
 }

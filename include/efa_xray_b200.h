@@ -183,7 +183,10 @@ int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx);
 
 /* ---- whole analysis with HOST buffers (one GPU) ------------------------------------------- */
 /* EnSRF(...).update() for callers that hold plain host arrays: uploads X, computes the ob priors,
- * runs the serial analysis, downloads the analysis ensemble.  fp64 throughout.
+ * runs the serial analysis, downloads the analysis ensemble.  fp64 throughout.  Internally a three-stream pipeline:
+ * the state is uploaded and downloaded in latitude bands that overlap the obs-space solve and the sweep of other
+ * bands; when X_host is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) and inflation == 1 the ob
+ * priors are gathered straight from host memory before the upload starts.
  *   X_host[nlev*ny*nx][nens]    in: prior ensemble; out: posterior ensemble (to_vect layout)
  *   lat/lon_deg[ny*nx]          2-D grid coordinates, row-major (y, x)
  *   ob_row0[nobs]               first state row of the ob's variable at its lower time level,
@@ -192,7 +195,9 @@ int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx);
  *   ob_diag[4][nobs]            out: prior_mean, prior_var, post_mean, post_var (ensrf.py:66-70,144-147)
  *   inflation                   multiplicative factor applied first (1.0 = none)
  *   stats[8]                    out, may be NULL: [0] sum|F_s| pairs, [1] sum|F_o| pairs, [2] n obs
- *                               within 1 km of a grid point, [3..6] ms: upload, setup, analysis, download */
+ *                               within 1 km of a grid point, [3..6] ms on the compute stream: geometry + stencils
+ *                               (+ host-memory gather), wait for the state / ob-prior split, obs-space solve +
+ *                               sweeps, download left exposed after the last sweep; [7] number of bands */
 int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int64_t nx, int nens,
                        const double *lat_deg, const double *lon_deg, int64_t nobs,
                        const double *ob_value, const double *ob_error, const double *ob_lat_deg,

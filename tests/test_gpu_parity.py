@@ -192,13 +192,19 @@ def test_fp32_tolerance():
     assert np.abs((p32 - m32[:, None]) - (ref_post - mref[:, None])).max() <= 1e-3 * spread
 
 
-def test_host_buffer_c_abi_entry():
-    """exb_ensrf_host_f64: plain host arrays in, posterior and diagnostics out."""
+@pytest.mark.parametrize('pinned', [False, True])
+def test_host_buffer_c_abi_entry(pinned):
+    """exb_ensrf_host_f64: plain host arrays in, posterior and diagnostics out; pageable and page-locked state
+    buffers take different routes through its upload / sweep / download pipeline."""
     import ctypes as C
+    import torch
     from efa_xray_b200 import _lib, engine
     g, p = load_golden('gc_multivar_offtime')
     case = make_case(**p['kw'])
     X = np.ascontiguousarray(case.to_vect())
+    if pinned:
+        keep = torch.from_numpy(X).pin_memory()
+        X = keep.numpy()
     ny, nx = case.lat2d.shape
     nt, nlev = len(case.times), len(case.varnames) * len(case.times)
     tlo, thi, wlo, whi, outside = engine.time_weights(case.times, case.ob_time)
