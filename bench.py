@@ -13,8 +13,10 @@ ensemble.  Three measurements share one JSON line:
             EnSRF.update() uses): pinned host state -> H2D -> analysis -> D2H, copies inside the timing
   cpu_baseline  the CPU oracle's per-observation loop on a bounded sample, rank 0, N = 1 only
 For N > 1 (launched by torchrun, one rank per GPU) the state is sharded in latitude bands; the obs-space
-solve is replicated; NCCL carries the all-reduce of the ob priors (value) and the scatter/gather of the
-bands (e2e).  Total work is fixed as N grows: "scaling": "strong".
+solve is replicated; NCCL carries the all-reduce of the ob priors.  In the e2e measurement the host-resident
+state is sharded the same way: every rank uploads and downloads its own band over its own PCIe link
+(sharding.scatter_bands / gather_bands remain for callers whose state lives on one rank).  Total work is
+fixed as N grows: "scaling": "strong".
 """
 import argparse
 import json
@@ -351,21 +353,17 @@ def run_ours(args):
     # ---- e2e: host buffers, copies inside the timed region ------------------------------------
     e2e = None
     if not args.no_e2e:
-        Oh = torch.empty_like(Xh).pin_memory() if rank == 0 else None
-        full = torch.empty((nrows, nens), dtype=tdtype, device=dev) if (rank == 0 and world > 1) else None
+        # host-resident state: at N = 1 one pinned buffer; at N > 1 sharded by latitude bands, every rank holds,
+        # uploads and downloads its own band (pinned) over its own PCIe link
+        if world == 1:
+            Xh_in, Oh = Xh, torch.empty_like(Xh).pin_memory()
+        else:
+            Xh_in = sharding.band_view(Xh, nlev, ny, nx, y0, y1).contiguous().reshape(-1, nens).pin_memory()
+            Oh = torch.empty_like(Xh_in).pin_memory()
 
         def e2e_step():
-            if world == 1:
-                return engine.analysis_host(Xh, nlev, case.lat2d, case.lon2d, obs, loc_mode, device=dev, dtype=tdtype,
-                                            grid=grid, out=Oh)
-            if rank == 0:
-                full.copy_(Xh, non_blocking=True)
-            Xb = sharding.scatter_bands(full, bands, nlev, ny, nx, nens, tdtype, dev, rank)
-            r = engine.analysis_device(Xb, nlev, grid, obs, loc_mode, band=band)
-            sharding.gather_bands(Xb, full, bands, nlev, ny, nx, nens, rank)
-            if rank == 0:
-                Oh.copy_(full, non_blocking=True)
-            return r
+            return engine.analysis_host(Xh_in, nlev, case.lat2d, case.lon2d, obs, loc_mode, device=dev, dtype=tdtype,
+                                        grid=grid, out=Oh, band=band)
 
         for _ in range(min(args.warmup, 2)):
             e2e_step()
@@ -390,9 +388,10 @@ def run_ours(args):
         ob_bytes = sum(getattr(obs, f).nbytes for f in ('value', 'error', 'lat', 'lon', 'halfwidth', 'assimilate',
                                                         'row0', 'row1', 'tw0', 'tw1')) + 2 * obs.nobs * 8
         e2e = {'value': nassim / (e2e_ms * 1e-3), 'unit': 'obs/s', 'ms_per_step': e2e_ms,
-               'h2d_bytes_per_step': int(Xh.numel() * 8 + ob_bytes),
+               'h2d_bytes_per_step': int(Xh.numel() * 8 + ob_bytes * world),
                'd2h_bytes_per_step': int(Xh.numel() * 8 + 8 * obs.nobs * 8 + 24),
-               'api': 'efa_xray_b200.engine.analysis_host (pinned host state in, pinned host analysis out)'}
+               'api': 'efa_xray_b200.engine.analysis_host (pinned host state in, pinned host analysis out%s)'
+                      % ('' if world == 1 else '; state sharded over the ranks by latitude band, each rank moves its own band')}
 
     if rank != 0:
         if world > 1:

@@ -33,6 +33,10 @@
 #define DG_LROWS (32 * DG_LWARPS) // rows per CTA of the list builder (one lane per row)
 #define DG_WARPS 4              // warps per CTA of the solve kernel
 #define DG_MINBLOCKS 8          // -> at most 64 registers per thread, 32 rows in flight per SM
+// measured on config 3: the tensor-pipe reduction below is no faster than the shuffle butterfly (18.6 vs 18.1 ms)
+#ifndef DG_DMMA_REDUCE
+#define DG_DMMA_REDUCE 0
+#endif
 #define DG_SENT 0xFFFFFFFFFFFFFFFFull
 #define DG_FULL 0xffffffffu
 #define DG_WATCHDOG (1u << 24)  // polls (>= 100 ns each once backed off) before a wait is declared dead
@@ -247,10 +251,36 @@ __device__ __forceinline__ unsigned long long dg_pack_scalar(double v) {
     return dg_hi(w) == 0xFFFFFFFFu ? 0x7FF8000000000000ull : w;
 }
 
-__device__ __forceinline__ double dg_warp_sum(double v) {
+__device__ __forceinline__ double dg_warp_sum_shfl(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DG_FULL, v, o);
     return v;
+}
+__device__ __forceinline__ void dg_dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// Sum of one value per lane, result in every lane, on the (otherwise idle) FP64 tensor pipe: the kernel is bound by
+// the load/store pipe, which also executes shuffles (10 SHFL for a 64-bit butterfly), and a DMMA chain has half the
+// latency of five shuffle levels.  m8n8k4 fragments: A[8x4] lane l -> A[l/4][l%4]; B[4x8] lane l -> B[l%4][l/4];
+// C[8x8] lane l -> C[l/4][2(l%4)], C[l/4][2(l%4)+1].
+//   1. A = v, B = 1            -> every lane of group r = l/4 holds R_r = sum of the group's 4 values
+//   2. A = [k == 0], B = R     -> lane l holds R_{2m}, R_{2m+1} (m = l%4), exactly;  u_m = R_{2m} + R_{2m+1}
+//   3. A = u (A[r][k] = u_k), B = 1 -> every lane holds u_0 + u_1 + u_2 + u_3
+__device__ __forceinline__ double dg_warp_sum(double v) {
+#if DG_DMMA_REDUCE
+    const int lane = threadIdx.x & 31;
+    double r0 = 0.0, r1 = 0.0;
+    dg_dmma(r0, r1, v, 1.0);
+    double p0 = 0.0, p1 = 0.0;
+    dg_dmma(p0, p1, (lane & 3) == 0 ? 1.0 : 0.0, r0);
+    const double u = p0 + p1;
+    double t0 = 0.0, t1 = 0.0;
+    dg_dmma(t0, t1, u, 1.0);
+    return t0;
+#else
+    return dg_warp_sum_shfl(v);
+#endif
 }
 
 // One published record as held by a lane: NW 64-bit words of the ye row + the two scalars

@@ -322,13 +322,16 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                           obs_pairs=int(cnt[0]), ms=tm.result())
 
 
-def sweep_band_schedule(nlev, ny, nx, nbands=6):
+def sweep_band_schedule(nlev, ny, nx, nbands=None):
     """Row ranges for a band-by-band sweep whose bands are uploaded / downloaded while other bands are swept:
     equal row counts (on a lat-lon grid every row has the same number of points, and with obs spread over the
     sphere every point sees about the same number of obs), edges on patch-row boundaries, the last band halved
     so that the download left exposed at the end is short.  The schedule only affects how well copies and
     kernels overlap."""
     g = max(1, int(_lib.load().exb_state_sweep_row_granularity(nlev, ny, nx)))
+    if nbands is None:
+        # every launch costs a tail and a small pre-pass: about 120 grid rows per band, at most 6 bands
+        nbands = max(1, min(6, ny // 120))
     nbands = max(1, min(nbands, ny // g if ny >= g else 1))
     edges = sorted(set([0, ny] + [int(round(ny * i / nbands / g)) * g for i in range(1, nbands)]))
     edges = [e for e in edges if 0 <= e <= ny]
@@ -340,14 +343,18 @@ def sweep_band_schedule(nlev, ny, nx, nbands=6):
 
 
 def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflation=None, device='cuda:0',
-                  dtype=None, grid=None, out=None, pipeline=True):
+                  dtype=None, grid=None, out=None, pipeline=True, band=None, group=None):
     """Host-buffer entry: X_host is a numpy array or CPU torch tensor [nlev*ny*nx, nens]; it is uploaded,
     analysed on `device`, and the analysis is written to `out` (default: back into X_host).  Pinned host
     memory makes the copies asynchronous.  With the fused float64 sweep (and pipeline=True) the state is swept
     in latitude bands and each finished band is downloaded on a second stream while the next one is swept, so
     only the last band's download is exposed; the upload is overlapped with the obs-space solve when X_host is
     pinned (see ob_priors).  res.ms gains 'upload' (duration of the host-to-device copies) and 'download' (what is
-    left of the device-to-host copies after the last sweep)."""
+    left of the device-to-host copies after the last sweep).
+
+    With band=(y0, y1) X_host / out hold only that latitude band of a host-resident state sharded over the ranks of
+    `group` (one process per GPU): every rank moves its own band over its own PCIe link, the partial ob priors are
+    all-reduced (NCCL), the obs-space solve is replicated and no other data crosses between ranks."""
     torch = _torch()
     _lib.require_device()
     Xh = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(X_host)
@@ -360,6 +367,8 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
             grid = GridTables(lat2d, lon2d, torch.device(device))
         nens = Xh.shape[1]
         xdtype = Xh.dtype if dtype is None else dtype
+        y0, y1 = band if band is not None else (0, grid.ny)
+        ny_loc = y1 - y0
         banded = (pipeline and fused_sweep_available(xdtype, nens) and Oh.dtype == xdtype and Xh.dtype == xdtype
                   and loc_mode == LOC_GC and obs.nobs > 0)
         if banded:
@@ -368,17 +377,17 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
             # while the state is still arriving; a band is swept as soon as it is on the device and downloaded
             # while the next ones are swept.
             copy_in, copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-            npts = grid.ny * grid.nx
+            npts = ny_loc * grid.nx
             X = torch.empty((nlev * npts, nens), dtype=xdtype, device=device)
             X3, H3, O3 = X.view(nlev, npts, nens), Xh.view(nlev, npts, nens), Oh.view(nlev, npts, nens)
-            bands = sweep_band_schedule(nlev, grid.ny, grid.nx)
+            bands = sweep_band_schedule(nlev, ny_loc, grid.nx)
             ev[0].record()
             obs_device = upload_obs(obs, torch.device(device), loc_mode)
             Y = None
             if inflation is None and Xh.is_pinned():
                 # PCIe is used by one thing at a time: first the gather (25 % of the state in 800-byte pieces),
                 # then the band uploads, which overlap the obs-space solve and the sweep of earlier bands
-                Y = ob_priors(Xh, grid, obs, _sfx(xdtype), nlev=nlev)
+                Y = ob_priors(Xh, grid, obs, _sfx(xdtype), nlev=nlev, band=band, group=group)
             arrived = {}
             copy_in.wait_stream(main)
             with torch.cuda.stream(copy_in):
@@ -404,7 +413,7 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
                     for lev in range(nlev):
                         O3[lev, ya * grid.nx:yb * grid.nx].copy_(X3[lev, ya * grid.nx:yb * grid.nx], non_blocking=True)
 
-            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation, Y=Y, sweep_bands=bands,
+            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation, Y=Y, sweep_bands=bands, band=band, group=group,
                                   before_band=wait_upload, on_band_done=download, obs_device=obs_device)
             ev[2].record()
             main.wait_stream(copy_out)
@@ -417,7 +426,7 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
             if dtype is not None and X.dtype != dtype:
                 X = X.to(dtype)
             ev[1].record()
-            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation)
+            res = analysis_device(X, nlev, grid, obs, loc_mode, inflation, band=band, group=group)
             ev[2].record()
             Oh.copy_(X.to(Oh.dtype) if X.dtype != Oh.dtype else X, non_blocking=True)
             ev[3].record()
