@@ -280,7 +280,8 @@ def run_ours(args):
     nlev = cfg['nvars'] * cfg['ntimes']
     ny, nx, nens = cfg['ny'], cfg['nx'], cfg['nmem']
     nrows = nlev * ny * nx
-    Xh = torch.empty((nrows, nens), dtype=torch.float64).pin_memory()
+    # the host-resident state has the storage type of the run (float32 runs: float32 storage, float64 arithmetic)
+    Xh = torch.empty((nrows, nens), dtype=tdtype).pin_memory()
     case, _ = build_case(args, out=Xh.numpy().reshape(cfg['nvars'], cfg['ntimes'], ny, nx, nens))
     obs = obs_arrays(case)
     nassim = int(obs.assimilate.sum())
@@ -388,8 +389,8 @@ def run_ours(args):
         ob_bytes = sum(getattr(obs, f).nbytes for f in ('value', 'error', 'lat', 'lon', 'halfwidth', 'assimilate',
                                                         'row0', 'row1', 'tw0', 'tw1')) + 2 * obs.nobs * 8
         e2e = {'value': nassim / (e2e_ms * 1e-3), 'unit': 'obs/s', 'ms_per_step': e2e_ms,
-               'h2d_bytes_per_step': int(Xh.numel() * 8 + ob_bytes * world),
-               'd2h_bytes_per_step': int(Xh.numel() * 8 + 8 * obs.nobs * 8 + 24),
+               'h2d_bytes_per_step': int(Xh.numel() * esize + ob_bytes * world),
+               'd2h_bytes_per_step': int(Xh.numel() * esize + 8 * obs.nobs * 8 + 24),
                'api': 'efa_xray_b200.engine.analysis_host (pinned host state in, pinned host analysis out%s)'
                       % ('' if world == 1 else '; state sharded over the ranks by latitude band, each rank moves its own band')}
 
@@ -433,7 +434,7 @@ def run_ours(args):
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
 
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.dtype == 'f64':
         del X, X0
         torch.cuda.empty_cache()
         state_gb = nrows * nens * 8 / 2 ** 30

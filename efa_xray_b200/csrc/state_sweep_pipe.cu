@@ -33,9 +33,9 @@
 #define SP_MAXSTAGES 16
 
 struct SpParams {
-    double *xm;                       // nullptr: fused mean/perturbation split + recombination
-    double *Xp;
-    const double *Yp;
+    void *xm;                         // nullptr: fused mean/perturbation split + recombination   (storage type TS)
+    void *Xp;                         // state rows, storage type TS (double or float); arithmetic is always double
+    const void *Yp;                   // ye rows, storage type TS
     const double *grid_u;
     const double *rec;
     const double *geo;
@@ -89,8 +89,11 @@ template <int NT3> __host__ __device__ constexpr int sp_yst() { return ((8 * NT3
 // Stage layout (doubles): y[8][YST] | om[G][8] | Gram[64] | ob[6][8] | count (one double slot, int inside)
 template <int NT3> __host__ __device__ constexpr int sp_stage_doubles(int G) { return 8 * sp_yst<NT3>() + 8 * G + 64 + 48 + 2; }
 
-template <int NT3>
+template <int NT3, typename TS>
 __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpParams p) {
+    TS *const gXp = static_cast<TS *>(p.Xp);
+    TS *const gxm = static_cast<TS *>(p.xm);
+    const TS *const gYp = static_cast<const TS *>(p.Yp);
     constexpr int YST = sp_yst<NT3>();
     constexpr int PC = 8 * NT3 - 1;          // column of the pseudo-member (the mean)
 
@@ -179,21 +182,47 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                 sc.c1 = __ldg(p.rec + REC_C1 * p.nobs + kk); sc.beta = __ldg(p.rec + REC_BETA * p.nobs + kk);
                 sc.innov = __ldg(p.rec + REC_INNOV * p.nobs + kk);
             }
+            if (sizeof(TS) == 8) {
 #pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-                double *dst = sy + q * YST;
-                const int sw = ((q >> 1) & 1) << 2;
-                if (q < nq) {
-                    const double *src = p.Yp + (int64_t)cand[q] * nens;
-                    if ((nens & 1) == 0) {
-                        for (int m = 2 * lane; m < nens; m += 64)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                for (int q = 0; q < 8; ++q) {
+                    double *dst = sy + q * YST;
+                    const int sw = ((q >> 1) & 1) << 2;
+                    if (q < nq) {
+                        const double *src8 = reinterpret_cast<const double *>(gYp) + (int64_t)cand[q] * nens;
+                        if ((nens & 1) == 0) {
+                            for (int m = 2 * lane; m < nens; m += 64)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src8 + m));
+                        } else {
+                            for (int m = lane; m < nens; m += 32)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src8 + m));
+                        }
                     } else {
-                        for (int m = lane; m < nens; m += 32)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp_smem(dst + (m ^ sw))), "l"(src + m));
+                        for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
                     }
-                } else {
-                    for (int m = lane; m < nens; m += 32) dst[m ^ sw] = 0.0;
+                }
+            } else {
+                // float32 storage: widen on the way into shared memory; all loads of the batch are issued before
+                // the first value is needed (8 rows x at most 4 values per lane: nens <= 8*NT3 - 1 <= 127)
+                constexpr int NCH = (8 * NT3 + 31) / 32;
+                float v[8][NCH];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const TS *src = gYp + (int64_t)cand[q < nq ? q : 0] * nens;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const int m = lane + 32 * j;
+                        v[q][j] = (q < nq && m < nens) ? (float)__ldg(src + m) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    double *dst = sy + q * YST;
+                    const int sw = ((q >> 1) & 1) << 2;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const int m = lane + 32 * j;
+                        if (m < nens) dst[m ^ sw] = (double)v[q][j];
+                    }
                 }
             }
             asm volatile("cp.async.commit_group;\n" ::);
@@ -388,7 +417,7 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             for (int h = 0; h < 2; ++h) {
                 const int m = 8 * t + 2 * c + h;
                 double v = 0.0;
-                if (active && m < nens) { v = p.Xp[row * nens + m]; sum += v; }
+                if (active && m < nens) { v = (double)gXp[row * nens + m]; sum += v; }
                 x[2 * t + h] = v;
             }
         }
@@ -407,7 +436,7 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             }
             if (c == 3) x[2 * NT3 - 1] = active ? mean : 0.0;
         } else if (c == 3) {
-            x[2 * NT3 - 1] = active ? p.xm[row] : 0.0;      // the mean rides along in the last column
+            x[2 * NT3 - 1] = active ? (double)gxm[row] : 0.0;      // the mean rides along in the last column
         }
     }
     bool dirty = false;
@@ -513,8 +542,8 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int m = 8 * t + 2 * c + h;
-                if (m < nens) p.Xp[row * nens + m] = x[2 * t + h] + mean;               // assimilation.py:168 when fused
-                else if (m == PC && !fused) p.xm[row] = x[2 * t + h];
+                if (m < nens) gXp[row * nens + m] = (TS)(x[2 * t + h] + mean);          // assimilation.py:168 when fused
+                else if (m == PC && !fused) gxm[row] = (TS)x[2 * t + h];
             }
         }
     }
@@ -626,7 +655,7 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int NT3>
+template <int NT3, typename TS>
 static int sp_launch(SpParams &p, cudaStream_t st) {
     const int Lc = p.nlev < SP_ROWS ? p.nlev : SP_ROWS;
     const int G = SP_ROWS / Lc;
@@ -655,7 +684,7 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     if (S < 2 * SP_PW) return EXB_ERR_UNSUPPORTED;
     p.nstages = S;
     const size_t smem = fixed + sizeof(double) * (size_t)S * p.stage_doubles;
-    EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // candidate lists per coarse tile (localised runs only; the kernel walks the ob range otherwise)
     float4 *caps = nullptr;
@@ -699,7 +728,7 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         exb_set_error("exb_state_sweep: too many patches for one launch");
         rc = EXB_ERR_ARG;
     } else if (nblocks > 0) {
-        state_sweep_pipe_kernel<NT3><<<(unsigned)nblocks, SP_NT, smem, st>>>(p);
+        state_sweep_pipe_kernel<NT3, TS><<<(unsigned)nblocks, SP_NT, smem, st>>>(p);
         exb_count_launches(1);
         rc = exb_check_launch("state_sweep_pipe_kernel");
     }
@@ -722,12 +751,14 @@ extern "C" int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t
     return bty;
 }
 
-// Called from state_update.cu for float64 states.  xm == nullptr selects the fused split/recombine mode (Xp then
-// holds full ensemble values).  Returns EXB_ERR_UNSUPPORTED if no variant fits.
-int exb_state_sweep_pipe_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
-                             const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
-                             const float4 *scan, int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin,
-                             int64_t y_end, int loc_mode, unsigned long long *counters, cudaStream_t st) {
+// Called from state_update.cu.  TS is the storage type of state and ye rows (float64, or float32 with float64
+// arithmetic in registers: every row is read and rounded back exactly once).  xm == nullptr selects the fused
+// split/recombine mode (Xp then holds full ensemble values).  Returns EXB_ERR_UNSUPPORTED if no variant fits.
+template <typename TS>
+int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
+                         const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
+                         int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                         cudaStream_t st) {
     SpParams p;
     p.xm = xm; p.Xp = Xp; p.Yp = Yp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
     p.tile_off = nullptr; p.tile_list = nullptr;
@@ -736,11 +767,18 @@ int exb_state_sweep_pipe_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, i
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
     p.role_split = getenv("EXB_SP_SPLIT") ? atoi(getenv("EXB_SP_SPLIT")) : 1;
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
-#define SP_TRY(N) if (need <= N) return sp_launch<N>(p, st)
+#define SP_TRY(N) if (need <= N) return sp_launch<N, TS>(p, st)
     SP_TRY(4);
     SP_TRY(7);
     SP_TRY(10);
     SP_TRY(13);
 #undef SP_TRY
-    return EXB_ERR_UNSUPPORTED;                       // larger ensembles: state_update_mma.cu (fewer registers per row)
+    return EXB_ERR_UNSUPPORTED;                       // larger ensembles: state_update_mma.cu / state_update.cu
 }
+
+template int exb_state_sweep_pipe<double>(double *, double *, int64_t, int64_t, int64_t, int, const double *, const double *,
+                                          const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
+                                          int64_t, int, unsigned long long *, cudaStream_t);
+template int exb_state_sweep_pipe<float>(float *, float *, int64_t, int64_t, int64_t, int, const double *, const float *,
+                                         const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
+                                         int64_t, int, unsigned long long *, cudaStream_t);

@@ -24,10 +24,11 @@ int exb_state_update_mma_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, i
                              const float4 *scan, int64_t nobs, int64_t ob_begin, int64_t ob_end, int loc_mode,
                              unsigned long long *counters, cudaStream_t st);
 
-int exb_state_sweep_pipe_f64(double *xm, double *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens,
-                             const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
-                             const float4 *scan, int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin,
-                             int64_t y_end, int loc_mode, unsigned long long *counters, cudaStream_t st);
+template <typename TS>
+int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
+                         const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
+                         int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                         cudaStream_t st);
 
 #define SU_NT 256
 #define SU_QCAP 16
@@ -350,21 +351,21 @@ static int state_update_impl(T *xm, T *Xp, int64_t nlev, int64_t ny, int64_t nx,
     EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
     exb_count_launches(1);
-    if (std::is_same<T, double>::value) {
-        // float64 states: FP64 tensor-core sweeps.  EXB_SU_IMPL = pipe (default: warp-specialised,
-        // state_sweep_pipe.cu) | mma (state_update_mma.cu, also the fallback for ensembles > 103 members) |
-        // vector (the kernel below)
+    {
+        // FP64 tensor-core sweeps (float32 states: float32 storage, float64 arithmetic in registers).
+        // EXB_SU_IMPL = pipe (default: warp-specialised, state_sweep_pipe.cu) | mma (state_update_mma.cu, float64
+        // only, also the fallback for ensembles > 103 members) | vector (the kernel below, arithmetic in T)
         const char *impl = getenv("EXB_SU_IMPL");
         const bool vec = impl && strcmp(impl, "vector") == 0, mma = impl && strcmp(impl, "mma") == 0;
         if (!vec && !mma) {
-            int rc = exb_state_sweep_pipe_f64((double *)xm, (double *)Xp, nlev, ny, nx, nens, grid_u, (const double *)Yp, rec,
-                                              obgeo, scan, nobs, ob_begin, ob_end, 0, ny, loc_mode, counters, st);
+            int rc = exb_state_sweep_pipe<T>(xm, Xp, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin, ob_end,
+                                             0, ny, loc_mode, counters, st);
             if (rc != EXB_ERR_UNSUPPORTED) {
                 cudaFreeAsync(scan, st);
                 return rc;
             }
         }
-        if (!vec) {
+        if (!vec && std::is_same<T, double>::value) {
             int rc = exb_state_update_mma_f64((double *)xm, (double *)Xp, nlev, ny, nx, nens, grid_u, (const double *)Yp,
                                               rec, obgeo, scan, nobs, ob_begin, ob_end, loc_mode, counters, st);
             if (rc != EXB_ERR_UNSUPPORTED) {
@@ -397,14 +398,14 @@ extern "C" int exb_state_update_f32(float *xm, float *Xp, int64_t nlev, int64_t 
                                     loc_mode, counters, stream);
 }
 
-// Fused sweep of grid rows [y_begin, y_end) of a float64 shard that holds FULL ensemble values: mean/perturbation
-// split (assimilation.py:146-147), the serial update of ensrf.py:95-141 and the recombination (assimilation.py:168)
-// in one pass over the touched rows.  Returns EXB_ERR_UNSUPPORTED when no fused variant exists for this ensemble
-// size (callers then use exb_split_mean_pert / exb_state_update / exb_recombine).
-extern "C" int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
-                                   const double *Yp, const double *rec, const double *obgeo, int64_t nobs,
-                                   int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode,
-                                   unsigned long long *counters, void *stream) {
+// Fused sweep of grid rows [y_begin, y_end) of a shard that holds FULL ensemble values: mean/perturbation split
+// (assimilation.py:146-147), the serial update of ensrf.py:95-141 and the recombination (assimilation.py:168) in one
+// pass over the touched rows.  Returns EXB_ERR_UNSUPPORTED when no fused variant exists for this ensemble size
+// (callers then use exb_split_mean_pert / exb_state_update / exb_recombine).
+template <typename T>
+static int state_sweep_impl(T *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const T *Yp,
+                            const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin, int64_t ob_end,
+                            int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters, void *stream) {
     EXB_REQUIRE(X && grid_u && Yp && rec && obgeo, "null pointer");
     EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nens >= 2 && nobs > 0, "bad sizes");
     EXB_REQUIRE(nlev < (1 << 30) && ny < (1 << 30) && nx < (1 << 30), "dimension too large");
@@ -417,8 +418,23 @@ extern "C" int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t 
     EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
     exb_count_launches(1);
-    const int rc = exb_state_sweep_pipe_f64(nullptr, X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin,
-                                            ob_end, y_begin, y_end, loc_mode, counters, st);
+    const int rc = exb_state_sweep_pipe<T>(nullptr, X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin,
+                                           ob_end, y_begin, y_end, loc_mode, counters, st);
     cudaFreeAsync(scan, st);
     return rc;
+}
+
+extern "C" int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                                   const double *Yp, const double *rec, const double *obgeo, int64_t nobs,
+                                   int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode,
+                                   unsigned long long *counters, void *stream) {
+    return state_sweep_impl<double>(X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, nobs, ob_begin, ob_end, y_begin, y_end,
+                                    loc_mode, counters, stream);
+}
+extern "C" int exb_state_sweep_f32(float *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                                   const float *Yp, const double *rec, const double *obgeo, int64_t nobs,
+                                   int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode,
+                                   unsigned long long *counters, void *stream) {
+    return state_sweep_impl<float>(X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, nobs, ob_begin, ob_end, y_begin, y_end,
+                                   loc_mode, counters, stream);
 }

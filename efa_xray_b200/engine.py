@@ -215,17 +215,17 @@ def state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, cou
                       ob_begin=0, ob_end=None):
     """Fused split + sweep + recombine of grid rows [y_begin, y_end) of a float64 shard holding full ensemble
     values (exb_state_sweep_f64)."""
-    _lib.call('exb_state_sweep_f64', _lib.ptr(X), nlev, ny, nx, X.shape[-1], _lib.ptr(grid_u), _lib.ptr(Yp),
+    _lib.call('exb_state_sweep_' + _sfx(X.dtype), _lib.ptr(X), nlev, ny, nx, X.shape[-1], _lib.ptr(grid_u), _lib.ptr(Yp),
               _lib.ptr(rec), _lib.ptr(geo), nobs, ob_begin, nobs if ob_end is None else ob_end, y_begin,
               ny if y_end is None else y_end, loc_mode, _lib.ptr(counters), _lib.stream_ptr())
 
 
 def fused_sweep_available(dtype, nens):
-    """The fused kernel exists for float64 ensembles of up to 103 members; EXB_FUSED=0 or EXB_SU_IMPL=mma|vector
+    """The fused kernel exists for float64 and float32 (storage) ensembles of up to 103 members; EXB_FUSED=0 or EXB_SU_IMPL=mma|vector
     select the three-call form (split, sweep, recombine)."""
     import os
     torch = _torch()
-    if dtype != torch.float64 or nens > 103 or os.environ.get('EXB_FUSED', '1') == '0':
+    if dtype not in (torch.float64, torch.float32) or nens > 103 or os.environ.get('EXB_FUSED', '1') == '0':
         return False
     return os.environ.get('EXB_SU_IMPL', 'pipe') == 'pipe'
 

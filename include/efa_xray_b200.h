@@ -165,15 +165,21 @@ int exb_state_update_f32(float *xm, float *Xp, int64_t nlev, int64_t ny, int64_t
                          int64_t nobs, int64_t ob_begin, int64_t ob_end, int loc_mode,
                          unsigned long long *counters, void *stream);
 
-/* Fused form of the state sweep for float64 shards that still hold FULL ensemble values (no exb_split_mean_pert
+/* Fused form of the state sweep for shards that still hold FULL ensemble values (no exb_split_mean_pert
  * before, no exb_recombine after): grid rows [y_begin, y_end) of the shard X[nlev][ny*nx][nens] are read once,
  * split into mean + perturbations in registers (assimilation/assimilation.py:146-147), updated by obs
  * [ob_begin, ob_end) in serial order (ensrf.py:95-141) and written back as mean + perturbations
  * (assimilation.py:168).  Rows no observation reaches are not written.  Bands of rows can be swept by separate
  * calls (e.g. to overlap the download of finished bands).  Synchronises the stream once (sizing of the candidate
- * lists).  Returns EXB_ERR_UNSUPPORTED for ensembles above 103 members (use the three-call form then). */
+ * lists).  Returns EXB_ERR_UNSUPPORTED for ensembles above 103 members (use the three-call form then).
+ * _f32: float32 STORAGE of state and ye rows; the arithmetic is float64 in registers (FP64 tensor cores), so each
+ * state value is rounded to float32 exactly once, when the analysis is written back. */
 int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
                         const double *Yp, const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin,
+                        int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                        void *stream);
+int exb_state_sweep_f32(float *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                        const float *Yp, const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin,
                         int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
                         void *stream);
 
