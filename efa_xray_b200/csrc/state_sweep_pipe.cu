@@ -25,8 +25,10 @@
 #include <cstring>
 #include <vector>
 
-#define SP_CW 12                      // consumer warps
-#define SP_PW 4                       // producer warps
+#ifndef SP_PW
+#define SP_PW 4                       // producer warps (on SM sub-partition 3: warps 3, 7, ...)
+#endif
+#define SP_CW (16 - SP_PW)            // consumer warps
 #define SP_NT ((SP_CW + SP_PW) * 32)
 #define SP_ROWS (SP_CW * 8)           // state rows per CTA
 #define SP_CT 4                       // coarse tile = SP_CT x SP_CT patches
@@ -87,9 +89,13 @@ __device__ __forceinline__ void sp_mbar_wait_empty(unsigned long long *bar, unsi
 template <int NT3> __host__ __device__ constexpr int sp_yst() { return ((8 * NT3) % 16 == 8) ? 8 * NT3 : 8 * NT3 + 8; }
 
 // Stage layout (doubles): y[8][YST] | om[G][8] | Gram[64] | ob[6][8] | count (one double slot, int inside)
-template <int NT3> __host__ __device__ constexpr int sp_stage_doubles(int G) { return 8 * sp_yst<NT3>() + 8 * G + 64 + 48 + 2; }
+// With MG the stage also carries, per grid point, the NEGATED 8x8 lower-triangular matrix M of the batch recurrence
+// (e = M g, see the consumer): | mneg[G][64]
+template <int NT3> __host__ __device__ constexpr int sp_stage_doubles(int G, bool mg) {
+    return 8 * sp_yst<NT3>() + 8 * G + 64 + 48 + 2 + (mg ? 64 * G : 0);
+}
 
-template <int NT3, typename TS>
+template <int NT3, typename TS, bool MG>
 __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpParams p) {
     TS *const gXp = static_cast<TS *>(p.Xp);
     TS *const gxm = static_cast<TS *>(p.xm);
@@ -103,8 +109,8 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_gu + 3 * SP_ROWS); // [SP_MAXSTAGES]
     unsigned long long *s_empty = s_full + SP_MAXSTAGES;                                      // [SP_MAXSTAGES]
     int *s_gvalid = reinterpret_cast<int *>(s_empty + SP_MAXSTAGES);                          // [SP_ROWS]
-    int *s_mine = s_gvalid + SP_ROWS;                                                         // [SP_PW][2][8]
-    int *s_scanbuf = s_mine + SP_PW * 16;                                                     // [SP_PW][128]
+    int *s_mine = s_gvalid + SP_ROWS;                                                         // [SP_PW][4][8]
+    int *s_scanbuf = s_mine + SP_PW * 32;                                                     // [SP_PW][128]
     __shared__ float s_bound[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -151,13 +157,20 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
     // share one issue port per sub-partition, arbitrated per instruction: a producer's 2-clock DFMA queued behind
     // three consumers' 16-clock DMMAs costs ~20-50 clocks.  With p.role_split the producers own sub-partition 3
     // (their localisation arithmetic then runs at the full scalar rate) and the consumers share the other three.
-    const bool is_producer = p.role_split ? ((warp & 3) == 3) : (warp >= SP_CW);
-    const int cw = p.role_split ? ((warp >> 2) * 3 + (warp & 3)) : warp;      // consumer index 0..11
+    // producers: the first SP_PW warps of sub-partition 3 (warps 3, 7, 11, 15); consumers: all others, numbered
+    // in warp order
+    const bool is_producer = p.role_split ? ((warp & 3) == 3 && (warp >> 2) < SP_PW) : (warp >= SP_CW);
+    int cw = warp;                        // consumer index 0..SP_CW-1
+    if (p.role_split) {
+        int before = (warp + 1) >> 2;     // warps of sub-partition 3 with a lower index
+        if (before > SP_PW) before = SP_PW;
+        cw = warp - before;
+    }
     if (is_producer) {
         // =============================== PRODUCER ===============================
         const int pw = p.role_split ? (warp >> 2) : (warp - SP_CW);
         const float bcx = s_bound[0], bcy = s_bound[1], bcz = s_bound[2], brho = s_bound[3];
-        int *mine = s_mine + pw * 16;
+        int *mine = s_mine + pw * 32;
         unsigned long long npairs = 0;
         const unsigned lt = (1u << lane) - 1u;
 
@@ -289,6 +302,31 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                     sG[n * 8 + 2 * c] = g0 + h0;
                     sG[n * 8 + 2 * c + 1] = g1 + h1;
                 }
+                if (MG) {
+                    // The 8-step recurrence  e_q = omega_q (g_q - sum_{p<q} G_qp e_p)  is linear in g: e = M g with M
+                    // lower triangular, M_jj = omega_j, M_qj = -omega_q sum_{j<=p<q} G_qp M_pj.  M depends on the grid
+                    // point (through omega) and on the batch (through G); computing it here, where scalar FP64 is
+                    // cheap, leaves the consumers two short dot products per lane instead of the serial chain.
+                    // One (grid point, column j) task at a time per lane; stored negated (the update subtracts).
+                    __syncwarp();
+                    double *sM = sob + 50;
+                    for (int t = lane; t < 8 * G; t += 32) {
+                        // column j of M for grid point gg = the recurrence applied to the unit vector e_j (uniform
+                        // code for every lane; entries above the diagonal come out as exact zeros)
+                        const int j = t & 7, gg = t >> 3;
+                        const double *om8 = som + gg * 8;
+                        double m[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            double acc = (q == j) ? 1.0 : 0.0;
+#pragma unroll
+                            for (int pp = 0; pp < q; ++pp) acc = fma(-sG[q * 8 + pp], m[pp], acc);
+                            m[q] = om8[q] * acc;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) sM[gg * 64 + q * 8 + j] = -m[q];
+                    }
+                }
             }
             if (lane == 0) *scnt = nq;
             __syncwarp();
@@ -319,7 +357,10 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
         while (true) {
             int emit_b = -1, emit_nq = 0;
             bool do_issue = false;
-            if (base < le || chunk < 4) {
+            if (nseen >= 8 * (bcur + 1)) {
+                // a complete batch of mine is waiting (one chunk of 32 entries can complete several)
+                emit_b = bcur; emit_nq = 8; do_issue = true;
+            } else if (base < le || chunk < 4) {
                 if (chunk == 4) {
                     // next group of four chunks: their index loads and record gathers are in flight together
                     int idx[4];
@@ -353,14 +394,15 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                 ++chunk;
                 const unsigned mask = __ballot_sync(0xffffffffu, v >= 0);
                 if (mask) {
+                    // up to 32 new candidates = parts of up to 5 batches, of which at most 3 are mine: the 4-deep
+                    // buffer keeps them apart (at most one earlier batch of mine is still incomplete)
                     if (v >= 0) {
                         const int seq = nseen + __popc(mask & lt);
                         const int bb = seq >> 3;
-                        if ((bb % SP_PW) == pw) mine[((bb / SP_PW) & 1) * 8 + (seq & 7)] = v;
+                        if ((bb % SP_PW) == pw) mine[((bb / SP_PW) & 3) * 8 + (seq & 7)] = v;
                     }
                     nseen += __popc(mask);
                     __syncwarp();
-                    if (nseen >= 8 * (bcur + 1)) { emit_b = bcur; emit_nq = 8; do_issue = true; }
                 }
             } else if (tail == 0) {
                 tail = 1;
@@ -377,7 +419,7 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             }
             if (emit_b == -1) continue;
             if (do_issue) {
-                issue(emit_b, emit_nq, mine + ((emit_b / SP_PW) & 1) * 8, new_sc);
+                issue(emit_b, emit_nq, mine + ((emit_b / SP_PW) & 3) * 8, new_sc);
                 if (emit_nq == 8) bcur += SP_PW;
                 else if (emit_nq > 0) bcur += SP_PW;
             }
@@ -494,6 +536,21 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                 if (c & 2) { gq[0] = r0; gq[1] = r1; gq[2] = r2; gq[3] = r3; gq[4] = q0; gq[5] = q1; gq[6] = q2; gq[7] = q3; }
                 else { gq[0] = q0; gq[1] = q1; gq[2] = q2; gq[3] = q3; gq[4] = r0; gq[5] = r1; gq[6] = r2; gq[7] = r3; }
             }
+            double ea0, ea1;
+            if (MG) {
+                // step 2: e = M g with the producers' per-grid-point matrix (stored negated): this lane needs
+                // -e_c (4 terms: M is lower triangular and c <= 3) and -e_{4+c} (8 terms)
+                const double *mr0 = Gb + 64 + 50 + gslot * 64 + c * 8;
+                const double *mr1 = mr0 + 32;
+                const double2 a0 = *reinterpret_cast<const double2 *>(mr0), a1 = *reinterpret_cast<const double2 *>(mr0 + 2);
+                const double2 b0 = *reinterpret_cast<const double2 *>(mr1), b1 = *reinterpret_cast<const double2 *>(mr1 + 2);
+                const double2 b2 = *reinterpret_cast<const double2 *>(mr1 + 4), b3 = *reinterpret_cast<const double2 *>(mr1 + 6);
+                const double s0 = fma(a0.y, gq[1], a0.x * gq[0]), s1 = fma(a1.y, gq[3], a1.x * gq[2]);
+                const double t0 = fma(b0.y, gq[1], b0.x * gq[0]), t1 = fma(b1.y, gq[3], b1.x * gq[2]);
+                const double t2 = fma(b2.y, gq[5], b2.x * gq[4]), t3 = fma(b3.y, gq[7], b3.x * gq[6]);
+                ea0 = active ? s0 + s1 : 0.0;
+                ea1 = active ? (t0 + t1) + (t2 + t3) : 0.0;
+            } else {
             // step 2: the serial recurrence inside the batch (per row; every lane of the row computes it)
             double e[8];
             e[0] = om[0] * gq[0];
@@ -513,10 +570,11 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
             e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
             e[6] = om[6] * (gq[6] - Gb[52] * e[4] - Gb[53] * e[5]);
             e[7] = om[7] * (gq[7] - Gb[60] * e[4] - Gb[61] * e[5] - Gb[62] * e[6]);
+            ea0 = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
+            ea1 = -((c == 0) ? e[4] : (c == 1) ? e[5] : (c == 2) ? e[6] : e[7]);
+            }
 
             // step 3: x[row][:] -= sum_q e_q y_q[:]   (A = -e in two k-steps, B = y, C = x)
-            const double ea0 = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
-            const double ea1 = -((c == 0) ? e[4] : (c == 1) ? e[5] : (c == 2) ? e[6] : e[7]);
             {
                 const int sw = ((c >> 1) & 1) << 2;                 // rows c and 4+c share this swizzle
                 const double *y0p = sy + c * YST + (n ^ sw);
@@ -655,7 +713,7 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int NT3, typename TS>
+template <int NT3, typename TS, bool MG>
 static int sp_launch(SpParams &p, cudaStream_t st) {
     const int Lc = p.nlev < SP_ROWS ? p.nlev : SP_ROWS;
     const int G = SP_ROWS / Lc;
@@ -672,19 +730,19 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     p.pr0 = p.y_begin / bty;
     const int pr1 = (p.y_end + bty - 1) / bty;              // patch rows [pr0, pr1)
     const int nty = pr1 - p.pr0;
-    p.stage_doubles = sp_stage_doubles<NT3>(p.G);
+    p.stage_doubles = sp_stage_doubles<NT3>(p.G, MG);
     int dev = 0, max_smem = 0;
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t fixed = sizeof(double) * 3 * SP_ROWS + sizeof(unsigned long long) * 2 * SP_MAXSTAGES +
-                         sizeof(int) * (SP_ROWS + SP_PW * 16 + SP_PW * 128) + 64;
+                         sizeof(int) * (SP_ROWS + SP_PW * 32 + SP_PW * 128) + 64;
     int S = (int)(((size_t)max_smem - 1024 - fixed) / (sizeof(double) * p.stage_doubles));
     if (S > SP_MAXSTAGES) S = SP_MAXSTAGES;
     S -= S % SP_PW;                    // every use of a stage is staged by the same producer warp (parity waits)
-    if (S < 2 * SP_PW) return EXB_ERR_UNSUPPORTED;
+    if (S < 8) return EXB_ERR_UNSUPPORTED;
     p.nstages = S;
     const size_t smem = fixed + sizeof(double) * (size_t)S * p.stage_doubles;
-    EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3, TS, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // candidate lists per coarse tile (localised runs only; the kernel walks the ob range otherwise)
     float4 *caps = nullptr;
@@ -728,7 +786,7 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         exb_set_error("exb_state_sweep: too many patches for one launch");
         rc = EXB_ERR_ARG;
     } else if (nblocks > 0) {
-        state_sweep_pipe_kernel<NT3, TS><<<(unsigned)nblocks, SP_NT, smem, st>>>(p);
+        state_sweep_pipe_kernel<NT3, TS, MG><<<(unsigned)nblocks, SP_NT, smem, st>>>(p);
         exb_count_launches(1);
         rc = exb_check_launch("state_sweep_pipe_kernel");
     }
@@ -767,7 +825,18 @@ int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, i
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
     p.role_split = getenv("EXB_SP_SPLIT") ? atoi(getenv("EXB_SP_SPLIT")) : 1;
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
-#define SP_TRY(N) if (need <= N) return sp_launch<N, TS>(p, st)
+    // The matrix form of the recurrence (MG) needs 64 more doubles per grid point and stage and ~290 more scalar FP64
+    // instructions per batch in the producers.  Measured on config 3: 202 ms against 160 ms for the chain form (the
+    // ring shrinks to 8 stages and the producers become the bottleneck again), so it is off unless EXB_SP_MG=1.
+    const bool want_mg = getenv("EXB_SP_MG") && atoi(getenv("EXB_SP_MG")) == 1;
+#define SP_TRY(N)                                                        \
+    if (need <= N) {                                                     \
+        if (want_mg) {                                                   \
+            const int rc = sp_launch<N, TS, true>(p, st);                \
+            if (rc != EXB_ERR_UNSUPPORTED) return rc;                    \
+        }                                                                \
+        return sp_launch<N, TS, false>(p, st);                           \
+    }
     SP_TRY(4);
     SP_TRY(7);
     SP_TRY(10);
