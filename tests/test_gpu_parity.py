@@ -504,3 +504,33 @@ def test_config3_full_size_properties():
     # (5) the whole analysis is finite and its spread did not grow on the sampled rows
     assert bool(torch.isfinite(X).all())
     assert (got.std(axis=1) <= prior[rows].std(axis=1) * (1 + 1e-9)).all()
+
+
+def test_edge_cases_skipped_single_and_polar_obs():
+    """Reference edge cases (ensrf.py:66-76): when every ob is skipped the state comes back unchanged and the prior
+    diagnostics are still recorded; a single ob; obs next to the poles and on the date line (largest footprints,
+    SURVEY 7.2) against the oracle."""
+    EnsembleState, Observation, EnSRF = _api()
+    case = make_case(ny=37, nx=72, nmem=20, nvars=2, ntimes=1, nobs=30, cutoff_km=2500.0, seed=61)
+    # (1) nothing assimilated
+    state, obs = build_objects(case, EnsembleState, Observation)
+    for o in obs:
+        o.assimilate_this = False
+    prior = state.to_vect().copy()
+    post, obs = EnSRF(state, obs, verbose=False, loc='GC').update()
+    np.testing.assert_array_equal(post.to_vect(), prior)
+    assert all(o.assimilated is False and o.prior_mean is not None and o.prior_var > 0 for o in obs)
+    # (2) a single ob
+    case1 = make_case(ny=37, nx=72, nmem=20, nvars=1, ntimes=1, nobs=1, cutoff_km=2500.0, seed=62)
+    state, obs = build_objects(case1, EnsembleState, Observation)
+    post, obs = EnSRF(state, obs, verbose=False, loc='GC').update()
+    ref_post, ref_obs = _oracle_run(case1, 'GC')
+    _check_post(post.to_vect(), ref_post, state.to_vect())
+    # (3) polar and date-line obs
+    case.ob_lat[:6] = [88.7, -88.9, 86.2, -87.4, 0.3, -0.7]
+    case.ob_lon[:6] = [12.3, 200.1, 359.2, 0.4, 359.6, 0.6]
+    state, obs = build_objects(case, EnsembleState, Observation)
+    post, obs = EnSRF(state, obs, verbose=False, loc='GC').update()
+    ref_post, ref_obs = _oracle_run(case, 'GC')
+    _check_post(post.to_vect(), ref_post, state.to_vect())
+    np.testing.assert_allclose(_diag(obs, 'post_var'), _diag(ref_obs, 'post_var'), rtol=1e-9, equal_nan=True)
