@@ -21,7 +21,7 @@
 template <typename T>
 int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                       const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
-                      unsigned long long *counters, cudaStream_t st, bool force);
+                      unsigned long long *counters, cudaStream_t st, bool force, void *plan);
 template <typename T>
 int exb_obs_solve_persistent(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                              const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
@@ -309,7 +309,7 @@ static int obs_solve_mc(T *Ym, T *Yp, const double *ob_value, const double *ob_e
 template <typename T>
 static int obs_solve_impl(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                           const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
-                          unsigned long long *counters, void *stream) {
+                          unsigned long long *counters, void *stream, void *plan = nullptr) {
     EXB_REQUIRE(Ym && Yp && ob_value && ob_error && ob_assim && geo && rec, "null pointer");
     EXB_REQUIRE(nobs > 0 && nens >= 2, "need nobs > 0 and nens >= 2");
     EXB_REQUIRE(loc_mode == EXB_LOC_NONE || loc_mode == EXB_LOC_GC, "bad loc_mode");
@@ -329,7 +329,7 @@ static int obs_solve_impl(T *Ym, T *Yp, const double *ob_value, const double *ob
         const bool want_dag = impl ? strcmp(impl, "dag") == 0 : loc_mode == EXB_LOC_GC;
         if (want_dag) {
             const int rc = exb_obs_solve_dag<T>(Ym, Yp, ob_value, ob_error, ob_assim, geo, nobs, nens, loc_mode, rec,
-                                                counters, st, impl != nullptr);
+                                                counters, st, impl != nullptr, plan);
             if (rc != EXB_ERR_UNSUPPORTED) return rc;
         }
         if (!(impl && strcmp(impl, "launches") == 0)) {
@@ -360,4 +360,16 @@ extern "C" int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, c
                                  const uint8_t *ob_assim, const double *obgeo, int64_t nobs, int nens,
                                  int loc_mode, double *rec, unsigned long long *counters, void *stream) {
     return obs_solve_impl<float>(Ym, Yp, ob_value, ob_error, ob_assim, obgeo, nobs, nens, loc_mode, rec, counters, stream);
+}
+
+// Same with a plan built earlier (exb_obs_plan_create), e.g. on a side stream while the ob priors were computed.
+extern "C" int exb_obs_solve_planned_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
+                                         const uint8_t *ob_assim, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                                         double *rec, unsigned long long *counters, void *stream) {
+    return obs_solve_impl<double>(Ym, Yp, ob_value, ob_error, ob_assim, obgeo, nobs, nens, loc_mode, rec, counters, stream, plan);
+}
+extern "C" int exb_obs_solve_planned_f32(void *plan, float *Ym, float *Yp, const double *ob_value, const double *ob_error,
+                                         const uint8_t *ob_assim, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                                         double *rec, unsigned long long *counters, void *stream) {
+    return obs_solve_impl<float>(Ym, Yp, ob_value, ob_error, ob_assim, obgeo, nobs, nens, loc_mode, rec, counters, stream, plan);
 }

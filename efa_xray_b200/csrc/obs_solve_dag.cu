@@ -44,7 +44,7 @@
 template <typename T>
 int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                       const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
-                      unsigned long long *counters, cudaStream_t st, bool force);
+                      unsigned long long *counters, cudaStream_t st, bool force, void *plan);
 
 __device__ __forceinline__ int64_t ceil_div64_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------
@@ -544,14 +544,148 @@ extern "C" int exb_obs_solve_async_status(void) {
     return EXB_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------------------------------
+// plan = everything that depends on the observation geometry only (predecessor lists).  It can be built on a side
+// stream while the ob priors are still being computed (exb_obs_plan_create) and is consumed by
+// exb_obs_solve_planned_*; exb_obs_solve_* builds a temporary one.
+// ------------------------------------------------------------------------------------------
+// Pinned staging buffer for the row offsets (reused; cudaHostAlloc is too slow to do per plan)
+static int64_t *g_off_pinned = nullptr;
+static size_t g_off_pinned_n = 0;
+static bool g_off_pinned_busy = false;
+
+struct ExbObsPlan {
+    int64_t nobs = 0;
+    int loc_mode = 0;
+    cudaStream_t st = nullptr;            // stream the plan was built on (its buffers are freed there)
+    float4 *pk = nullptr;
+    int64_t *off = nullptr;
+    int *list = nullptr;                  // filled when all lists fit one block, else built per block at solve time
+    std::vector<int64_t> off_h;
+    bool dense = false;                   // dependency graph too dense for the dependency-driven solve to pay
+    int64_t budget = 0;
+    cudaEvent_t ready = nullptr, used = nullptr;
+    bool was_used = false;
+    bool finished = false, uses_pinned = false;
+};
+
+static int dg_pool_setup() {
+    if (g_status_host) return EXB_OK;
+    // work buffers come from the stream-ordered pool; keep freed blocks cached instead of returning them to
+    // the driver at every synchronisation (a 0.5 GB list costs ~20 ms to re-allocate otherwise)
+    int dev = 0;
+    cudaMemPool_t pool;
+    EXB_CUDA(cudaGetDevice(&dev));
+    EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    EXB_CUDA(cudaHostAlloc(&g_status_host, sizeof(int), cudaHostAllocMapped));
+    EXB_CUDA(cudaHostGetDevicePointer(&g_status_dev, g_status_host, 0));
+    return EXB_OK;
+}
+
+static void dg_plan_free(ExbObsPlan *pl) {
+    if (!pl) return;
+    if (pl->uses_pinned) { cudaStreamSynchronize(pl->st); g_off_pinned_busy = false; }
+    if (pl->was_used && pl->used) cudaStreamWaitEvent(pl->st, pl->used, 0);
+    if (pl->pk) cudaFreeAsync(pl->pk, pl->st);
+    if (pl->off) cudaFreeAsync(pl->off, pl->st);
+    if (pl->list) cudaFreeAsync(pl->list, pl->st);
+    if (pl->ready) cudaEventDestroy(pl->ready);
+    if (pl->used) cudaEventDestroy(pl->used);
+    delete pl;
+}
+
+// Step 1 (asynchronous): enqueues packing, the count pass, the prefix sum and the download of the row offsets on st.
+static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, cudaStream_t st, ExbObsPlan **out) {
+    *out = nullptr;
+    if (nobs >= 0x7fffffff) return EXB_ERR_UNSUPPORTED;
+    const int rc0 = dg_pool_setup();
+    if (rc0 != EXB_OK) return rc0;
+    ExbObsPlan *pl = new ExbObsPlan();
+    pl->nobs = nobs; pl->loc_mode = loc_mode; pl->st = st;
+    struct Guard { ExbObsPlan *p; ~Guard() { if (p) dg_plan_free(p); } } guard{pl};
+    int *cnt = nullptr;
+    EXB_CUDA(cudaEventCreateWithFlags(&pl->ready, cudaEventDisableTiming));
+    EXB_CUDA(cudaEventCreateWithFlags(&pl->used, cudaEventDisableTiming));
+    EXB_CUDA(cudaMallocAsync(&pl->pk, (size_t)nobs * sizeof(float4), st));
+    EXB_CUDA(cudaMallocAsync(&pl->off, (size_t)(nobs + 1) * sizeof(int64_t), st));
+    EXB_CUDA(cudaMallocAsync(&cnt, (size_t)nobs * sizeof(int), st));
+    dag_pack_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(geo, ob_assim, nobs, loc_mode, pl->pk);
+    dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+        pl->pk, 0, nobs, cnt, nullptr, 0, nullptr);
+    dag_scan_kernel<<<1, 1024, 0, st>>>(cnt, nobs, pl->off);
+    exb_count_launches(3);
+    cudaFreeAsync(cnt, st);
+    EXB_CUDA(cudaGetLastError());
+    pl->off_h.resize((size_t)nobs + 1);
+    if (!g_off_pinned_busy) {
+        if (g_off_pinned_n < (size_t)nobs + 1) {
+            if (g_off_pinned) cudaFreeHost(g_off_pinned);
+            g_off_pinned = nullptr;
+            g_off_pinned_n = 0;
+            EXB_CUDA(cudaHostAlloc(&g_off_pinned, ((size_t)nobs + 1) * sizeof(int64_t), cudaHostAllocDefault));
+            g_off_pinned_n = (size_t)nobs + 1;
+        }
+        pl->uses_pinned = true;
+        g_off_pinned_busy = true;
+        EXB_CUDA(cudaMemcpyAsync(g_off_pinned, pl->off, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    } else {
+        EXB_CUDA(cudaMemcpyAsync(pl->off_h.data(), pl->off, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    guard.p = nullptr;
+    *out = pl;
+    return EXB_OK;
+}
+
+// Step 2: waits for the offsets (synchronises the plan's stream), sizes and fills the lists.
+static int dg_plan_finish(ExbObsPlan *pl) {
+    if (pl->finished) return EXB_OK;
+    const int64_t nobs = pl->nobs;
+    cudaStream_t st = pl->st;
+    EXB_CUDA(cudaStreamSynchronize(st));
+    if (pl->uses_pinned) {
+        memcpy(pl->off_h.data(), g_off_pinned, ((size_t)nobs + 1) * sizeof(int64_t));
+        g_off_pinned_busy = false;
+        pl->uses_pinned = false;
+    }
+    const double nnz = (double)pl->off_h[(size_t)nobs];
+    const double dense = 0.5 * (double)nobs * (double)(nobs - 1);
+    pl->dense = nobs > 2048 && nnz > 0.5 * dense;
+    pl->budget = (int64_t)1 << 30;                                      // list entries per row block (4 GiB)
+    if (const char *e = getenv("EXB_DAG_BUDGET")) {
+        const long long v = atoll(e);
+        if (v > 0) pl->budget = v;
+    }
+    if (!pl->dense && pl->off_h[(size_t)nobs] > 0 && pl->off_h[(size_t)nobs] <= pl->budget) {
+        EXB_CUDA(cudaMallocAsync(&pl->list, (size_t)pl->off_h[(size_t)nobs] * sizeof(int), st));
+        dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+            pl->pk, 0, nobs, nullptr, pl->off, 0, pl->list);
+        exb_count_launches(1);
+        EXB_CUDA(cudaGetLastError());
+    }
+    EXB_CUDA(cudaEventRecord(pl->ready, st));
+    pl->finished = true;
+    return EXB_OK;
+}
+
+static int dg_plan_build(const double *geo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, cudaStream_t st, ExbObsPlan **out) {
+    const int rc = dg_plan_begin(geo, ob_assim, nobs, loc_mode, st, out);
+    if (rc != EXB_OK) return rc;
+    const int rc2 = dg_plan_finish(*out);
+    if (rc2 != EXB_OK) { dg_plan_free(*out); *out = nullptr; }
+    return rc2;
+}
+
 template <typename T, int MC>
-static int dg_run(DgArgs<T> a, const float4 *pk, const std::vector<int64_t> &off_h, int64_t budget, cudaStream_t st) {
+static int dg_run(DgArgs<T> a, const ExbObsPlan &pl, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     EXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag_solve_kernel<T, MC>, DG_WARPS * 32, 0));
     if (per_sm < 1) return EXB_ERR_UNSUPPORTED;
     const int64_t nobs = a.nobs;
+    const std::vector<int64_t> &off_h = pl.off_h;
     AsyncBuf P(st), S(st), list(st), ticket(st);
     const size_t p_bytes = (size_t)nobs * 32 * MC * sizeof(T), s_bytes = (size_t)nobs * 2 * sizeof(double);
     EXB_CUDA(P.alloc(p_bytes));
@@ -562,26 +696,31 @@ static int dg_run(DgArgs<T> a, const float4 *pk, const std::vector<int64_t> &off
     a.P = P.as<T>();
     a.S = S.as<double>();
     a.ticket = ticket.as<int>();
-    // row blocks whose predecessor lists fit the budget
+    a.off = pl.off;
+    // row blocks whose predecessor lists fit the budget (one block, filled by the plan, in the usual case)
     int64_t r0 = 0, max_block = 0;
     std::vector<std::pair<int64_t, int64_t>> blocks;
-    while (r0 < nobs) {
-        int64_t r1 = r0 + 1;
-        while (r1 < nobs && off_h[r1 + 1] - off_h[r0] <= budget) ++r1;
-        blocks.push_back({r0, r1});
-        if (off_h[r1] - off_h[r0] > max_block) max_block = off_h[r1] - off_h[r0];
-        r0 = r1;
+    if (pl.list || off_h[(size_t)nobs] == 0) {
+        blocks.push_back({0, nobs});
+    } else {
+        while (r0 < nobs) {
+            int64_t r1 = r0 + 1;
+            while (r1 < nobs && off_h[r1 + 1] - off_h[r0] <= pl.budget) ++r1;
+            blocks.push_back({r0, r1});
+            if (off_h[r1] - off_h[r0] > max_block) max_block = off_h[r1] - off_h[r0];
+            r0 = r1;
+        }
+        EXB_CUDA(list.alloc((size_t)max_block * sizeof(int)));
     }
-    EXB_CUDA(list.alloc((size_t)max_block * sizeof(int)));
-    a.list = list.as<int>();
+    a.list = pl.list ? pl.list : list.as<int>();
     for (auto &b : blocks) {
         a.row_begin = b.first;
         a.row_end = b.second;
         a.list_base = off_h[b.first];
         const int64_t nrows = b.second - b.first;
-        if (off_h[b.second] > off_h[b.first]) {
+        if (!pl.list && off_h[b.second] > off_h[b.first]) {
             dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-                pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>());
+                pl.pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>());
             exb_count_launches(1);
         }
         EXB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(int), st));
@@ -595,57 +734,66 @@ static int dg_run(DgArgs<T> a, const float4 *pk, const std::vector<int64_t> &off
 }
 
 // force = false: returns EXB_ERR_UNSUPPORTED when the dependency graph is too dense for this method to pay
-// (the caller then uses the panel kernel).
+// (the caller then uses the panel kernel).  plan may be null (a temporary one is built on st).
 template <typename T>
 int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
                       const double *geo, int64_t nobs, int nens, int loc_mode, double *rec,
-                      unsigned long long *counters, cudaStream_t st, bool force) {
-    if (nobs >= 0x7fffffff) return EXB_ERR_UNSUPPORTED;
-    if (!g_status_host) {
-        // work buffers come from the stream-ordered pool; keep freed blocks cached instead of returning them to
-        // the driver at every synchronisation (a 0.5 GB list costs ~20 ms to re-allocate otherwise)
-        int dev = 0;
-        cudaMemPool_t pool;
-        EXB_CUDA(cudaGetDevice(&dev));
-        EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
-        EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        EXB_CUDA(cudaHostAlloc(&g_status_host, sizeof(int), cudaHostAllocMapped));
-        EXB_CUDA(cudaHostGetDevicePointer(&g_status_dev, g_status_host, 0));
+                      unsigned long long *counters, cudaStream_t st, bool force, void *plan_in) {
+    ExbObsPlan *pl = static_cast<ExbObsPlan *>(plan_in), *tmp = nullptr;
+    if (!pl) {
+        const int rc = dg_plan_build(geo, ob_assim, nobs, loc_mode, st, &tmp);
+        if (rc != EXB_OK) return rc;
+        pl = tmp;
+    } else {
+        if (pl->nobs != nobs || pl->loc_mode != loc_mode) {
+            exb_set_error("exb_obs_solve: the plan was built for another observation set");
+            return EXB_ERR_ARG;
+        }
+        const int rcf = dg_plan_finish(pl);
+        if (rcf != EXB_OK) return rcf;
+        EXB_CUDA(cudaStreamWaitEvent(st, pl->ready, 0));
     }
+    struct TmpGuard { ExbObsPlan *p; ~TmpGuard() { if (p) dg_plan_free(p); } } tguard{tmp};
+    if (!force && pl->dense) return EXB_ERR_UNSUPPORTED;
     *g_status_host = 0;
-    AsyncBuf pk(st), cnt(st), off(st);
-    EXB_CUDA(pk.alloc((size_t)nobs * sizeof(float4)));
-    EXB_CUDA(cnt.alloc((size_t)nobs * sizeof(int)));
-    EXB_CUDA(off.alloc((size_t)(nobs + 1) * sizeof(int64_t)));
-    dag_pack_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(geo, ob_assim, nobs, loc_mode, pk.as<float4>());
-    dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-        pk.as<float4>(), 0, nobs, cnt.as<int>(), nullptr, 0, nullptr);
-    dag_scan_kernel<<<1, 1024, 0, st>>>(cnt.as<int>(), nobs, off.as<int64_t>());
-    exb_count_launches(3);
-    EXB_CUDA(cudaGetLastError());
-    std::vector<int64_t> off_h((size_t)nobs + 1);
-    EXB_CUDA(cudaMemcpyAsync(off_h.data(), off.p, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    EXB_CUDA(cudaStreamSynchronize(st));
-    const double nnz = (double)off_h[(size_t)nobs];
-    const double dense = 0.5 * (double)nobs * (double)(nobs - 1);
-    if (!force && nobs > 2048 && nnz > 0.5 * dense) return EXB_ERR_UNSUPPORTED;
-    int64_t budget = (int64_t)1 << 30;                                  // list entries per row block (4 GiB)
-    if (const char *e = getenv("EXB_DAG_BUDGET")) {
-        const long long v = atoll(e);
-        if (v > 0) budget = v;
-    }
     DgArgs<T> a;
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
-    a.counters = counters; a.off = off.as<int64_t>(); a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
+    a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
     a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
     a.loc_mode = loc_mode;
-    if (nens <= 128) return dg_run<T, 4>(a, pk.as<float4>(), off_h, budget, st);
-    if (nens <= 256) return dg_run<T, 8>(a, pk.as<float4>(), off_h, budget, st);
-    return EXB_ERR_UNSUPPORTED;
+    int rc = EXB_ERR_UNSUPPORTED;
+    if (nens <= 128) rc = dg_run<T, 4>(a, *pl, st);
+    else if (nens <= 256) rc = dg_run<T, 8>(a, *pl, st);
+    if (!tmp) {
+        cudaEventRecord(pl->used, st);
+        pl->was_used = true;
+    } else {
+        // the temporary plan's buffers are freed on st, after the kernels above
+        tmp->was_used = false;
+    }
+    return rc;
+}
+
+extern "C" int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, void *stream,
+                                   void **plan) {
+    EXB_REQUIRE(obgeo && ob_assim && plan && nobs > 0, "null pointer or nobs <= 0");
+    ExbObsPlan *pl = nullptr;
+    const int rc = dg_plan_begin(obgeo, ob_assim, nobs, loc_mode, (cudaStream_t)stream, &pl);
+    *plan = pl;
+    return rc;
+}
+
+extern "C" int exb_obs_plan_finish(void *plan) {
+    EXB_REQUIRE(plan, "null plan");
+    return dg_plan_finish(static_cast<ExbObsPlan *>(plan));
+}
+
+extern "C" int exb_obs_plan_destroy(void *plan) {
+    dg_plan_free(static_cast<ExbObsPlan *>(plan));
+    return EXB_OK;
 }
 
 template int exb_obs_solve_dag<double>(double *, double *, const double *, const double *, const uint8_t *, const double *,
-                                       int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool);
+                                       int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool, void *);
 template int exb_obs_solve_dag<float>(float *, float *, const double *, const double *, const uint8_t *, const double *,
-                                      int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool);
+                                      int64_t, int, int, double *, unsigned long long *, cudaStream_t, bool, void *);

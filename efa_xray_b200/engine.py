@@ -199,10 +199,46 @@ class _Timer:
         return out
 
 
-def obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx):
+def obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=None):
+    if plan is not None:
+        _lib.call('exb_obs_solve_planned_' + sfx, plan.handle, _lib.ptr(Ym), _lib.ptr(Yp), _lib.ptr(obs_dev['value']),
+                  _lib.ptr(obs_dev['error']), _lib.ptr(obs_dev['assimilate']), _lib.ptr(geo), Ym.shape[0], nens,
+                  loc_mode, _lib.ptr(rec), _lib.ptr(counters), _lib.stream_ptr())
+        return
     _lib.call('exb_obs_solve_' + sfx, _lib.ptr(Ym), _lib.ptr(Yp), _lib.ptr(obs_dev['value']),
               _lib.ptr(obs_dev['error']), _lib.ptr(obs_dev['assimilate']), _lib.ptr(geo), Ym.shape[0], nens,
               loc_mode, _lib.ptr(rec), _lib.ptr(counters), _lib.stream_ptr())
+
+
+class ObsPlan:
+    """The geometry-only part of the obs-space solve (predecessor lists), built on a side stream while the host and
+    the current stream compute the ob priors: the constructor only enqueues the counting pass (exb_obs_plan_create),
+    finish() sizes the lists and enqueues the fill pass (exb_obs_plan_finish)."""
+
+    def __init__(self, obs_dev, geo, nobs, loc_mode):
+        torch = _torch()
+        self.handle = C.c_void_p()
+        self.stream = torch.cuda.Stream(device=geo.device)
+        ready = obs_dev.get('_ready')
+        if ready is not None:
+            self.stream.wait_event(ready)
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream())
+        _lib.call('exb_obs_plan_create', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode,
+                  C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
+
+    def finish(self):
+        _lib.call('exb_obs_plan_finish', self.handle)
+
+    def destroy(self):
+        if self.handle:
+            _lib.call('exb_obs_plan_destroy', self.handle)
+            self.handle = C.c_void_p()
+
+
+def obs_plan_wanted(loc_mode):
+    import os
+    return loc_mode == LOC_GC and os.environ.get('EXB_OBS_IMPL', 'dag') == 'dag' and os.environ.get('EXB_OBS_PLAN', '1') != '0'
 
 
 def state_update(xm, Xp, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, counters, sfx, ob_begin=0, ob_end=None):
@@ -243,6 +279,8 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
     geo = torch.empty((8, obs.nobs), dtype=torch.float64, device=device)
     _lib.call('exb_obs_prepare', _lib.ptr(d['lat']), _lib.ptr(d['lon']), _lib.ptr(d['halfwidth']), obs.nobs,
               loc_mode, _lib.ptr(geo), _lib.stream_ptr())
+    d['_ready'] = torch.cuda.Event()
+    d['_ready'].record()
     return d, geo
 
 
@@ -282,6 +320,9 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         # (small host-to-device copies: callers that stream the state in on another stream do them first and pass
         # the result, or they would queue behind the state in the copy engine)
         obs_dev, geo = obs_device if obs_device is not None else upload_obs(obs, dev, loc_mode)
+        # predecessor lists of the obs-space solve: geometry only, started on a side stream now so that they are built
+        # while the host and this stream work on the ob priors
+        plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode) if obs_plan_wanted(loc_mode) else None
         if Y is None:
             Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group)
         elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
@@ -294,10 +335,12 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         if not fused:
             xm = torch.empty(nrows, dtype=X.dtype, device=dev)
             _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+        if plan is not None:
+            plan.finish()
         tm.mark('setup')
         rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
         counters = torch.zeros(2, dtype=torch.int64, device=dev)
-        obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx)
+        obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
         tm.mark('obs_solve')
         grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
         if fused:
@@ -314,6 +357,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
         tm.mark('recombine')
         rec_h = rec.cpu().numpy()
+        if plan is not None:
+            plan.destroy()
         _lib.call('exb_obs_solve_async_status')
         cnt = counters.cpu().numpy()
         nex_h = int(nex.item())

@@ -141,6 +141,24 @@ int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, const double
                       const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
                       int loc_mode, double *rec, unsigned long long *counters, void *stream);
 
+/* The part of exb_obs_solve_* that depends on the observation geometry only (the predecessor lists of the
+ * dependency-driven solve) can be built ahead, on another stream, while the ob priors are still being computed:
+ * exb_obs_plan_create only enqueues (packing, counting pass, prefix sum) on ITS stream and returns an opaque plan;
+ * exb_obs_plan_finish synchronises that stream, sizes the lists and enqueues the fill pass (it is implied by the
+ * first exb_obs_solve_planned_* if not called); exb_obs_solve_planned_* makes its stream wait for the plan; exb_obs_plan_destroy frees the plan (its buffers are
+ * released in stream order after the last solve that used it).  A plan fits the (obgeo, ob_assimilate, nobs,
+ * loc_mode) it was built from. */
+int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assimilate, int64_t nobs, int loc_mode, void *stream,
+                        void **plan);
+int exb_obs_plan_finish(void *plan);
+int exb_obs_plan_destroy(void *plan);
+int exb_obs_solve_planned_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
+                              const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
+                              int loc_mode, double *rec, unsigned long long *counters, void *stream);
+int exb_obs_solve_planned_f32(void *plan, float *Ym, float *Yp, const double *ob_value, const double *ob_error,
+                              const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
+                              int loc_mode, double *rec, unsigned long long *counters, void *stream);
+
 /* exb_obs_solve_* only enqueues its kernels (the dependency-driven variant synchronises the stream once, to size
  * its work lists, before the solve itself is launched).  Its kernels wait on each other inside the launch; a
  * watchdog ends a wait that can never be satisfied (corrupted inputs) instead of hanging the device.  After
