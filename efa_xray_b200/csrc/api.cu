@@ -319,7 +319,7 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     std::vector<int64_t> edges;
     if (fused) {
         const int64_t g = exb_state_sweep_row_granularity(nlev, ny, nx);
-        int64_t nb = 6;
+        int64_t nb = ny / 180 < 1 ? 1 : (ny / 180 > 6 ? 6 : ny / 180);
         if (nb > ny / g) nb = ny / g > 0 ? ny / g : 1;
         edges.push_back(0);
         for (int64_t i = 1; i < nb; ++i) {

@@ -48,7 +48,8 @@ struct SpParams {
     int64_t npts, nobs, ob_begin, ob_end;
     int nlev, ny, nx, nens;
     int y_begin, y_end;               // grid rows [y_begin, y_end) of the shard are swept by this launch
-    int pr0;                          // first patch row of this launch
+    int eq_row;                       // grid row of the shard closest to the equator (-1: unknown, keep row order)
+    int pr0, npr, pr_eq;              // first patch row / number of patch rows of this launch, patch row of the equator
     int ty, tx, ntx, nctx;            // patch shape, patches along x, coarse tiles along x
     int G, Lc, nlc;
     int loc_mode;
@@ -59,6 +60,11 @@ struct SpParams {
 __device__ __forceinline__ void sp_dmma(double &c0, double &c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// volatile variant: keeps the program order of a sequence of DMMAs (the compiler may not re-pair them)
+__device__ __forceinline__ void sp_dmma_v(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ unsigned sp_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(unsigned long long *bar, unsigned count) {
@@ -120,7 +126,19 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
 
     const int lc = blockIdx.x % p.nlc;
     const int tile = blockIdx.x / p.nlc;
-    const int prow = p.pr0 + tile / p.ntx, pcol = tile % p.ntx;
+    // Patch rows are issued heaviest first: on a lat-lon grid the rows next to the poles meet the most candidate
+    // obs (their grid points are closer together than the obs), so they must not be the tail of the launch.  Rows are
+    // taken alternately from the two ends of the launch's range when it straddles the equator, else from the
+    // poleward end.
+    int prow;
+    {
+        const int r = tile / p.ntx, nr = p.npr, eq = p.pr_eq;
+        if (eq < 0) prow = p.pr0 + r;
+        else if (eq <= p.pr0) prow = p.pr0 + nr - 1 - r;
+        else if (eq >= p.pr0 + nr) prow = p.pr0 + r;
+        else prow = (r & 1) ? p.pr0 + nr - 1 - (r >> 1) : p.pr0 + (r >> 1);
+    }
+    const int pcol = tile % p.ntx;
     const int y0 = prow * p.ty, x0 = pcol * p.tx;
     const int l0 = lc * Lc;
 
@@ -579,11 +597,12 @@ __global__ void __launch_bounds__(SP_NT, 1) state_sweep_pipe_kernel(const SpPara
                 const int sw = ((c >> 1) & 1) << 2;                 // rows c and 4+c share this swizzle
                 const double *y0p = sy + c * YST + (n ^ sw);
                 const double *y1p = y0p + 4 * YST;
+                // all tiles with obs 0..3 first, then all with obs 4..7: a tile's second DMMA depends on its first
+                // (26 clocks), back to back it would stall the warp's in-order issue
 #pragma unroll
-                for (int t = 0; t < NT3; ++t) {
-                    sp_dmma(x[2 * t], x[2 * t + 1], ea0, y0p[8 * t]);
-                    sp_dmma(x[2 * t], x[2 * t + 1], ea1, y1p[8 * t]);
-                }
+                for (int t = 0; t < NT3; ++t) sp_dmma_v(x[2 * t], x[2 * t + 1], ea0, y0p[8 * t]);
+#pragma unroll
+                for (int t = 0; t < NT3; ++t) sp_dmma_v(x[2 * t], x[2 * t + 1], ea1, y1p[8 * t]);
             }
             dirty = true;
         }
@@ -679,6 +698,25 @@ __global__ void sweep_tile_list_kernel(const float4 *__restrict__ caps, int ntil
     }
 }
 
+// grid row of [y_begin, y_end) closest to the equator (|sin lat| of its first column smallest) -> mapped host word
+__global__ void sweep_eq_row_kernel(const double *__restrict__ uz, int nx, int y_begin, int y_end, long long *__restrict__ out) {
+    __shared__ double bv[256];
+    __shared__ int bi[256];
+    double best = 2.0;
+    int besty = y_begin;
+    for (int y = y_begin + threadIdx.x; y < y_end; y += 256) {
+        const double v = fabs(uz[(int64_t)y * nx]);
+        if (v < best) { best = v; besty = y; }
+    }
+    bv[threadIdx.x] = best; bi[threadIdx.x] = besty;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && bv[threadIdx.x + o] < bv[threadIdx.x]) { bv[threadIdx.x] = bv[threadIdx.x + o]; bi[threadIdx.x] = bi[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = bi[0];
+}
+
 // exclusive prefix sum of cnt[n] into off[n+1], n small (one CTA, serial over chunks of 1024)
 __global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict__ cnt, int n, int64_t *__restrict__ off,
                                                          long long *__restrict__ total_host) {
@@ -730,6 +768,8 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     p.pr0 = p.y_begin / bty;
     const int pr1 = (p.y_end + bty - 1) / bty;              // patch rows [pr0, pr1)
     const int nty = pr1 - p.pr0;
+    p.npr = nty;
+    p.pr_eq = p.eq_row >= 0 ? p.eq_row / bty : -1;
     p.stage_doubles = sp_stage_doubles<NT3>(p.G, MG);
     int dev = 0, max_smem = 0;
     EXB_CUDA(cudaGetDevice(&dev));
@@ -764,13 +804,16 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, cnt, nullptr, nullptr);
         static long long *total_host = nullptr, *total_dev = nullptr;
         if (!total_host) {
-            EXB_CUDA(cudaHostAlloc(&total_host, sizeof(long long), cudaHostAllocMapped));
+            EXB_CUDA(cudaHostAlloc(&total_host, 2 * sizeof(long long), cudaHostAllocMapped));
             EXB_CUDA(cudaHostGetDevicePointer(&total_dev, total_host, 0));
         }
         sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off, total_dev);
-        exb_count_launches(3);
+        sweep_eq_row_kernel<<<1, 256, 0, st>>>(p.grid_u + 2 * p.npts, p.nx, p.y_begin, p.y_end, total_dev + 1);
+        exb_count_launches(4);
         EXB_CUDA(cudaStreamSynchronize(st));
         const long long total = *reinterpret_cast<volatile long long *>(total_host);
+        p.eq_row = (int)*reinterpret_cast<volatile long long *>(total_host + 1);
+        p.pr_eq = p.eq_row / bty;
         EXB_CUDA(cudaMallocAsync(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
         sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, nullptr, off, list);
         exb_count_launches(1);
@@ -823,6 +866,7 @@ int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, i
     p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;
     p.nlev = (int)nlev; p.ny = (int)ny; p.nx = (int)nx; p.nens = nens; p.loc_mode = loc_mode;
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
+    p.eq_row = -1;
     p.role_split = getenv("EXB_SP_SPLIT") ? atoi(getenv("EXB_SP_SPLIT")) : 1;
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
     // The matrix form of the recurrence (MG) needs 64 more doubles per grid point and stage and ~290 more scalar FP64

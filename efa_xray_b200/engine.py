@@ -375,8 +375,8 @@ def sweep_band_schedule(nlev, ny, nx, nbands=None):
     kernels overlap."""
     g = max(1, int(_lib.load().exb_state_sweep_row_granularity(nlev, ny, nx)))
     if nbands is None:
-        # every launch costs a tail and a small pre-pass: about 120 grid rows per band, at most 6 bands
-        nbands = max(1, min(6, ny // 120))
+        # every launch costs a tail and a small pre-pass: about 180 grid rows per band, at most 6 bands
+        nbands = max(1, min(6, ny // 180))
     nbands = max(1, min(nbands, ny // g if ny >= g else 1))
     edges = sorted(set([0, ny] + [int(round(ny * i / nbands / g)) * g for i in range(1, nbands)]))
     edges = [e for e in edges if 0 <= e <= ny]
