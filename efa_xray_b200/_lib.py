@@ -34,7 +34,10 @@ SIGNATURES = {
     'exb_obs_solve_f32': [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],
     'exb_obs_solve_async_status': [],
     'exb_obs_plan_create': [_p, _p, _i64, _int, _p, _p],
+    'exb_obs_plan_create_dist': [_p, _p, _i64, _int, _int, _int, _p, _p],
     'exb_obs_plan_finish': [_p],
+    'exb_obs_solve_dist_f64': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _int, _int, _p, _p, _p],
+    'exb_obs_solve_dist_f32': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _int, _int, _p, _p, _p],
     'exb_obs_plan_destroy': [_p],
     'exb_obs_solve_planned_f64': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],
     'exb_obs_solve_planned_f32': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],

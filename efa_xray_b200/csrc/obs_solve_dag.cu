@@ -82,7 +82,10 @@ __global__ void dag_pack_kernel(const double *__restrict__ geo, const uint8_t *_
 template <bool FILL>
 __global__ void __launch_bounds__(DG_LWARPS * 32)
 dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_end, int *__restrict__ cnt,
-                const int64_t *__restrict__ off, int64_t list_base, int *__restrict__ list) {
+                const int64_t *__restrict__ off, int64_t list_base, int *__restrict__ list, int stride, int first) {
+    // [row_begin, row_end) are indices v into the rows this process solves: ob index j = first + v * stride
+    // (stride 1, first 0: all rows; the distributed solve builds the lists of its own rows only).  cnt / off / the
+    // list segments are indexed by v.
     __shared__ float4 tile[DG_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Row block b costs ~b: a CTA takes block blockIdx.x and its mirror image, so every CTA has the same work.
@@ -90,16 +93,17 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
     for (int half = 0; half < 2; ++half) {
     const int64_t blk = half == 0 ? (int64_t)blockIdx.x : nblk - 1 - (int64_t)blockIdx.x;
     if (half == 1 && blk <= (int64_t)blockIdx.x) break;
-    const int64_t j0 = row_begin + blk * DG_LROWS;
-    const int64_t jw = j0 + warp * 32;                                // first row of this warp
-    const int64_t j = jw + lane;
-    const bool valid = j < row_end;
-    const int64_t jtop = (j0 + DG_LROWS < row_end ? j0 + DG_LROWS : row_end) - 1;    // last row of this CTA
+    const int64_t v0 = row_begin + blk * DG_LROWS;
+    const int64_t vw = v0 + warp * 32, v = vw + lane;
+    const int64_t jw = first + vw * stride;                           // first row of this warp
+    const int64_t j = first + v * stride;
+    const bool valid = v < row_end;
+    const int64_t jtop = first + ((v0 + DG_LROWS < row_end ? v0 + DG_LROWS : row_end) - 1) * stride;    // last row of this CTA
     const float qnan = __int_as_float(0x7fc00000);                    // rows past the end: every test is false
     float4 me = make_float4(qnan, qnan, qnan, 0.f);
     if (valid) me = pk[j];
     int *out = list;
-    if (FILL && valid) out = list + (off[j] - list_base);
+    if (FILL && valid) out = list + (off[v] - list_base);
     int count = 0;
     for (int64_t t0 = 0; t0 < jtop; t0 += DG_TILE) {
         __syncthreads();
@@ -108,7 +112,7 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
             tile[i] = (k < jtop) ? pk[k] : make_float4(0.f, 0.f, 0.f, 3.0f);
         }
         __syncthreads();
-        if (jw >= row_end) continue;
+        if (vw >= row_end) continue;
         // candidates k < jw precede every row of the warp
         const int64_t rem = jw - t0;
         const int full = rem <= 0 ? 0 : (rem < DG_TILE ? (int)rem : DG_TILE);
@@ -122,7 +126,7 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
             }
         }
         // the warp's own 32 rows: k < j per lane
-        const int64_t last = jw + 31 - t0;
+        const int64_t last = jw + 31 * (int64_t)stride - t0;
         const int lim = last < DG_TILE ? (int)last : DG_TILE;
         for (int i = full; i < lim; ++i) {
             const float4 q = tile[i];
@@ -133,7 +137,7 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
             }
         }
     }
-    if (!FILL && valid) cnt[j] = count;
+    if (!FILL && valid) cnt[v] = count;
     }
 }
 
@@ -197,6 +201,11 @@ struct DgArgs {
     int *status;                 // != 0: watchdog fired
     int64_t nobs, row_begin, row_end;
     int nens, loc_mode;
+    // distributed variant (DIST): rows j with j % world == rank are solved here; records are published into the P / S
+    // buffers of every GPU of the group (peer memory over NVLink), readers always poll their own copy
+    int world, rank;
+    void *P_peer[8];
+    void *S_peer[8];
 };
 
 __device__ __forceinline__ void dg_ld16(const void *p, unsigned long long &a, unsigned long long &b) {
@@ -213,6 +222,15 @@ __device__ __forceinline__ void dg_ld32(const void *p, unsigned long long &a, un
 __device__ __forceinline__ void dg_st32(void *p, unsigned long long a, unsigned long long b, unsigned long long c,
                                         unsigned long long d) {
     asm volatile("st.relaxed.gpu.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// system-scope stores for records published into peer memory
+__device__ __forceinline__ void dg_st16_sys(void *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void dg_st32_sys(void *p, unsigned long long a, unsigned long long b, unsigned long long c,
+                                            unsigned long long d) {
+    asm volatile("st.relaxed.sys.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
 // The sentinel is recognised by 32 bits per element: the high half of a double / the whole float equal to
@@ -395,7 +413,7 @@ __device__ __forceinline__ bool dg_step(const DgArgs<T> &a, int lane, DgRow<T, M
     return more;
 }
 
-template <typename T, int MC>
+template <typename T, int MC, bool DIST>
 __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(const DgArgs<T> a) {
     constexpr int NW = DgCfg<T, MC>::NW;
     constexpr int PER = DgWord<T>::PER;
@@ -410,7 +428,8 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         int t = 0;
         if (lane == 0) t = atomicAdd(a.ticket, 1);
         t = __shfl_sync(DG_FULL, t, 0);
-        const int64_t j = a.row_begin + t;
+        int64_t j = a.row_begin + t;
+        if (DIST) j = a.rank + (int64_t)t * a.world;      // t-th row of this rank (row_begin is 0 when distributed)
         if (j >= a.row_end) break;
 
         // ---- this row: perturbations (lane owns members [MC*lane, MC*lane+MC)), mean, geometry ----
@@ -423,7 +442,8 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         r.mj = (double)__ldcg(a.Ym + j);
         r.dead = false;
         const double ux = a.geo[GEO_UX * nobs + j], uy = a.geo[GEO_UY * nobs + j], uz = a.geo[GEO_UZ * nobs + j];
-        const int64_t lb = a.off[j] - a.list_base, le = a.off[j + 1] - a.list_base;
+        const int64_t oi = DIST ? (int64_t)t : j;       // lists are indexed by the rank's own row number when distributed
+        const int64_t lb = a.off[oi] - a.list_base, le = a.off[oi + 1] - a.list_base;
 
         // ---- predecessors, 32 at a time: weights lane-parallel, updates strictly in list order ----
         int kl_next = (lb + lane < le) ? __ldg(a.list + lb + lane) : -1;
@@ -472,20 +492,43 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
 
         // publish (data first, the polled word last); skipped obs are never anyone's predecessor
         if (act) {
-            unsigned long long *p = reinterpret_cast<unsigned long long *>(a.P + (j * 32 + lane) * MC);
             unsigned long long pw[NW];
-            if (lane * MC < nens) {
 #pragma unroll
             for (int c = 0; c < NW; ++c) pw[c] = DgWord<T>::pack(r.x + c * PER);
-            if constexpr (NW % 4 == 0) {
+            const unsigned long long s0 = dg_pack_scalar(c1 * innov), s1 = dg_pack_scalar(c1 * beta);
+            if (!DIST) {
+                unsigned long long *p = reinterpret_cast<unsigned long long *>(a.P + (j * 32 + lane) * MC);
+                if (lane * MC < nens) {
+                    if constexpr (NW % 4 == 0) {
 #pragma unroll
-                for (int c = 0; c < NW; c += 4) dg_st32(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
+                        for (int c = 0; c < NW; c += 4) dg_st32(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NW; c += 2) dg_st16(p + c, pw[c], pw[c + 1]);
+                    }
+                }
+                if (lane == 0) dg_st16(a.S + j * 2, s0, s1);
             } else {
+                // own copy first (local readers are the closest in index), then the peers
+                for (int q = 0; q < a.world; ++q) {
+                    const int dst = (a.rank + q) % a.world;
+                    unsigned long long *p = reinterpret_cast<unsigned long long *>(static_cast<T *>(a.P_peer[dst]) + (j * 32 + lane) * MC);
+                    if (lane * MC < nens) {
+                        if constexpr (NW % 4 == 0) {
 #pragma unroll
-                for (int c = 0; c < NW; c += 2) dg_st16(p + c, pw[c], pw[c + 1]);
+                            for (int c = 0; c < NW; c += 4) dg_st32_sys(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NW; c += 2) dg_st16_sys(p + c, pw[c], pw[c + 1]);
+                        }
+                    }
+                }
+                if (lane == 0)
+                    for (int q = 0; q < a.world; ++q) {
+                        const int dst = (a.rank + q) % a.world;
+                        dg_st16_sys(static_cast<double *>(a.S_peer[dst]) + j * 2, s0, s1);
+                    }
             }
-            }
-            if (lane == 0) dg_st16(a.S + j * 2, dg_pack_scalar(c1 * innov), dg_pack_scalar(c1 * beta));
         }
         // outputs of the C ABI: ye_j / mye_j in place, per-ob records
 #pragma unroll
@@ -557,6 +600,8 @@ static bool g_off_pinned_busy = false;
 struct ExbObsPlan {
     int64_t nobs = 0;
     int loc_mode = 0;
+    int stride = 1, first = 0;            // rows of this plan: first + v * stride (distributed solve: world, rank)
+    int64_t nrows = 0;                    // number of those rows
     cudaStream_t st = nullptr;            // stream the plan was built on (its buffers are freed there)
     float4 *pk = nullptr;
     int64_t *off = nullptr;
@@ -597,28 +642,33 @@ static void dg_plan_free(ExbObsPlan *pl) {
 }
 
 // Step 1 (asynchronous): enqueues packing, the count pass, the prefix sum and the download of the row offsets on st.
-static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, cudaStream_t st, ExbObsPlan **out) {
+static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, cudaStream_t st, ExbObsPlan **out,
+                         int stride = 1, int first = 0) {
     *out = nullptr;
     if (nobs >= 0x7fffffff) return EXB_ERR_UNSUPPORTED;
     const int rc0 = dg_pool_setup();
     if (rc0 != EXB_OK) return rc0;
     ExbObsPlan *pl = new ExbObsPlan();
     pl->nobs = nobs; pl->loc_mode = loc_mode; pl->st = st;
+    pl->stride = stride; pl->first = first;
+    pl->nrows = first < nobs ? (nobs - first + stride - 1) / stride : 0;
+    const int64_t nrows = pl->nrows > 0 ? pl->nrows : 1;
     struct Guard { ExbObsPlan *p; ~Guard() { if (p) dg_plan_free(p); } } guard{pl};
     int *cnt = nullptr;
     EXB_CUDA(cudaEventCreateWithFlags(&pl->ready, cudaEventDisableTiming));
     EXB_CUDA(cudaEventCreateWithFlags(&pl->used, cudaEventDisableTiming));
     EXB_CUDA(cudaMallocAsync(&pl->pk, (size_t)nobs * sizeof(float4), st));
-    EXB_CUDA(cudaMallocAsync(&pl->off, (size_t)(nobs + 1) * sizeof(int64_t), st));
-    EXB_CUDA(cudaMallocAsync(&cnt, (size_t)nobs * sizeof(int), st));
+    EXB_CUDA(cudaMallocAsync(&pl->off, (size_t)(nrows + 1) * sizeof(int64_t), st));
+    EXB_CUDA(cudaMallocAsync(&cnt, (size_t)nrows * sizeof(int), st));
     dag_pack_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(geo, ob_assim, nobs, loc_mode, pl->pk);
-    dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-        pl->pk, 0, nobs, cnt, nullptr, 0, nullptr);
-    dag_scan_kernel<<<1, 1024, 0, st>>>(cnt, nobs, pl->off);
+    EXB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nrows * sizeof(int), st));
+    dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+        pl->pk, 0, pl->nrows, cnt, nullptr, 0, nullptr, stride, first);
+    dag_scan_kernel<<<1, 1024, 0, st>>>(cnt, nrows, pl->off);
     exb_count_launches(3);
     cudaFreeAsync(cnt, st);
     EXB_CUDA(cudaGetLastError());
-    pl->off_h.resize((size_t)nobs + 1);
+    pl->off_h.resize((size_t)nrows + 1);
     if (!g_off_pinned_busy) {
         if (g_off_pinned_n < (size_t)nobs + 1) {
             if (g_off_pinned) cudaFreeHost(g_off_pinned);
@@ -629,9 +679,9 @@ static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nob
         }
         pl->uses_pinned = true;
         g_off_pinned_busy = true;
-        EXB_CUDA(cudaMemcpyAsync(g_off_pinned, pl->off, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        EXB_CUDA(cudaMemcpyAsync(g_off_pinned, pl->off, (size_t)(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     } else {
-        EXB_CUDA(cudaMemcpyAsync(pl->off_h.data(), pl->off, (size_t)(nobs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        EXB_CUDA(cudaMemcpyAsync(pl->off_h.data(), pl->off, (size_t)(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
     guard.p = nullptr;
     *out = pl;
@@ -641,26 +691,26 @@ static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nob
 // Step 2: waits for the offsets (synchronises the plan's stream), sizes and fills the lists.
 static int dg_plan_finish(ExbObsPlan *pl) {
     if (pl->finished) return EXB_OK;
-    const int64_t nobs = pl->nobs;
+    const int64_t nobs = pl->nobs, nrows = pl->nrows > 0 ? pl->nrows : 1;
     cudaStream_t st = pl->st;
     EXB_CUDA(cudaStreamSynchronize(st));
     if (pl->uses_pinned) {
-        memcpy(pl->off_h.data(), g_off_pinned, ((size_t)nobs + 1) * sizeof(int64_t));
+        memcpy(pl->off_h.data(), g_off_pinned, ((size_t)nrows + 1) * sizeof(int64_t));
         g_off_pinned_busy = false;
         pl->uses_pinned = false;
     }
-    const double nnz = (double)pl->off_h[(size_t)nobs];
-    const double dense = 0.5 * (double)nobs * (double)(nobs - 1);
-    pl->dense = nobs > 2048 && nnz > 0.5 * dense;
+    const int64_t total = pl->off_h[(size_t)nrows];
+    const double dense = 0.5 * (double)nobs * (double)(nobs - 1) / (double)pl->stride;
+    pl->dense = nobs > 2048 && (double)total > 0.5 * dense;
     pl->budget = (int64_t)1 << 30;                                      // list entries per row block (4 GiB)
     if (const char *e = getenv("EXB_DAG_BUDGET")) {
         const long long v = atoll(e);
         if (v > 0) pl->budget = v;
     }
-    if (!pl->dense && pl->off_h[(size_t)nobs] > 0 && pl->off_h[(size_t)nobs] <= pl->budget) {
-        EXB_CUDA(cudaMallocAsync(&pl->list, (size_t)pl->off_h[(size_t)nobs] * sizeof(int), st));
-        dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nobs, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-            pl->pk, 0, nobs, nullptr, pl->off, 0, pl->list);
+    if (!pl->dense && total > 0 && total <= pl->budget) {
+        EXB_CUDA(cudaMallocAsync(&pl->list, (size_t)total * sizeof(int), st));
+        dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
+            pl->pk, 0, pl->nrows, nullptr, pl->off, 0, pl->list, pl->stride, pl->first);
         exb_count_launches(1);
         EXB_CUDA(cudaGetLastError());
     }
@@ -677,30 +727,36 @@ static int dg_plan_build(const double *geo, const uint8_t *ob_assim, int64_t nob
     return rc2;
 }
 
-template <typename T, int MC>
+template <typename T, int MC, bool DIST>
 static int dg_run(DgArgs<T> a, const ExbObsPlan &pl, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    EXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag_solve_kernel<T, MC>, DG_WARPS * 32, 0));
+    EXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag_solve_kernel<T, MC, DIST>, DG_WARPS * 32, 0));
     if (per_sm < 1) return EXB_ERR_UNSUPPORTED;
     const int64_t nobs = a.nobs;
     const std::vector<int64_t> &off_h = pl.off_h;
     AsyncBuf P(st), S(st), list(st), ticket(st);
-    const size_t p_bytes = (size_t)nobs * 32 * MC * sizeof(T), s_bytes = (size_t)nobs * 2 * sizeof(double);
-    EXB_CUDA(P.alloc(p_bytes));
-    EXB_CUDA(S.alloc(s_bytes));
-    EXB_CUDA(cudaMemsetAsync(P.p, 0xFF, p_bytes, st));
-    EXB_CUDA(cudaMemsetAsync(S.p, 0xFF, s_bytes, st));
+    if (!DIST) {
+        const size_t p_bytes = (size_t)nobs * 32 * MC * sizeof(T), s_bytes = (size_t)nobs * 2 * sizeof(double);
+        EXB_CUDA(P.alloc(p_bytes));
+        EXB_CUDA(S.alloc(s_bytes));
+        EXB_CUDA(cudaMemsetAsync(P.p, 0xFF, p_bytes, st));
+        EXB_CUDA(cudaMemsetAsync(S.p, 0xFF, s_bytes, st));
+        a.P = P.as<T>();
+        a.S = S.as<double>();
+    } else {
+        // the caller owns the (symmetric) buffers, has filled them with the sentinel and synchronised the group
+        a.P = static_cast<T *>(a.P_peer[a.rank]);
+        a.S = static_cast<double *>(a.S_peer[a.rank]);
+    }
     EXB_CUDA(ticket.alloc(sizeof(int)));
-    a.P = P.as<T>();
-    a.S = S.as<double>();
     a.ticket = ticket.as<int>();
     a.off = pl.off;
     // row blocks whose predecessor lists fit the budget (one block, filled by the plan, in the usual case)
     int64_t r0 = 0, max_block = 0;
     std::vector<std::pair<int64_t, int64_t>> blocks;
-    if (pl.list || off_h[(size_t)nobs] == 0) {
+    if (pl.list || off_h.back() == 0) {
         blocks.push_back({0, nobs});
     } else {
         while (r0 < nobs) {
@@ -716,18 +772,18 @@ static int dg_run(DgArgs<T> a, const ExbObsPlan &pl, cudaStream_t st) {
     for (auto &b : blocks) {
         a.row_begin = b.first;
         a.row_end = b.second;
-        a.list_base = off_h[b.first];
+        a.list_base = DIST ? 0 : off_h[b.first];
         const int64_t nrows = b.second - b.first;
-        if (!pl.list && off_h[b.second] > off_h[b.first]) {
+        if (!pl.list && !DIST && off_h[b.second] > off_h[b.first]) {
             dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-                pl.pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>());
+                pl.pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>(), 1, 0);
             exb_count_launches(1);
         }
         EXB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(int), st));
         int64_t grid = (int64_t)sms * per_sm;
-        const int64_t need = ceil_div64(nrows, DG_WARPS);
+        const int64_t need = ceil_div64(DIST ? ceil_div64(nrows, a.world) + 1 : nrows, DG_WARPS);
         if (grid > need) grid = need;
-        dag_solve_kernel<T, MC><<<(unsigned)grid, DG_WARPS * 32, 0, st>>>(a);
+        dag_solve_kernel<T, MC, DIST><<<(unsigned)grid, DG_WARPS * 32, 0, st>>>(a);
         exb_count_launches(1);
     }
     return exb_check_launch("dag_solve_kernel");
@@ -745,8 +801,8 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
         if (rc != EXB_OK) return rc;
         pl = tmp;
     } else {
-        if (pl->nobs != nobs || pl->loc_mode != loc_mode) {
-            exb_set_error("exb_obs_solve: the plan was built for another observation set");
+        if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->stride != 1) {
+            exb_set_error("exb_obs_solve: the plan was built for another observation set (or for a distributed solve)");
             return EXB_ERR_ARG;
         }
         const int rcf = dg_plan_finish(pl);
@@ -761,9 +817,11 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
     a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
     a.loc_mode = loc_mode;
+    a.world = 1; a.rank = 0;
+    for (int q = 0; q < 8; ++q) { a.P_peer[q] = nullptr; a.S_peer[q] = nullptr; }
     int rc = EXB_ERR_UNSUPPORTED;
-    if (nens <= 128) rc = dg_run<T, 4>(a, *pl, st);
-    else if (nens <= 256) rc = dg_run<T, 8>(a, *pl, st);
+    if (nens <= 128) rc = dg_run<T, 4, false>(a, *pl, st);
+    else if (nens <= 256) rc = dg_run<T, 8, false>(a, *pl, st);
     if (!tmp) {
         cudaEventRecord(pl->used, st);
         pl->was_used = true;
@@ -774,11 +832,74 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
     return rc;
 }
 
+// Distributed obs-space solve: rank `rank` of `world` (<= 8 GPUs of one NVLink domain) solves the rows j with
+// j % world == rank and publishes their records into the P / S buffers of every rank (P_peers / S_peers: device
+// pointers valid on THIS device, e.g. torch symmetric memory; P: nobs*32*MC elements of T with MC = 4 up to 128
+// members, 8 above; S: nobs*2 doubles).  Preconditions: all buffers filled with 0xFF bytes and the group synchronised
+// after that; every rank calls this with the same inputs.  Outputs (Ym, Yp, rec, counters[0]) are written for the
+// rank's own rows only: the caller zeroes the others and sums over the group.
+template <typename T>
+static int dg_solve_dist(void *plan, T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
+                         const double *geo, int64_t nobs, int nens, int loc_mode, double *rec, unsigned long long *counters,
+                         int rank, int world, void *const *P_peers, void *const *S_peers, cudaStream_t st) {
+    EXB_REQUIRE(plan && Ym && Yp && ob_value && ob_error && ob_assim && geo && rec && P_peers && S_peers, "null pointer");
+    EXB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank / world");
+    ExbObsPlan *pl = static_cast<ExbObsPlan *>(plan);
+    if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->stride != world || pl->first != rank) {
+        exb_set_error("exb_obs_solve_dist: the plan was built for another observation set, rank or group size");
+        return EXB_ERR_ARG;
+    }
+    const int rcf = dg_plan_finish(pl);
+    if (rcf != EXB_OK) return rcf;
+    if (pl->dense || (!pl->list && pl->off_h.back() > 0)) return EXB_ERR_UNSUPPORTED;
+    EXB_CUDA(cudaStreamWaitEvent(st, pl->ready, 0));
+    *g_status_host = 0;
+    DgArgs<T> a;
+    a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
+    a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
+    a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
+    a.loc_mode = loc_mode;
+    a.world = world; a.rank = rank;
+    for (int q = 0; q < 8; ++q) { a.P_peer[q] = q < world ? P_peers[q] : nullptr; a.S_peer[q] = q < world ? S_peers[q] : nullptr; }
+    int rc = EXB_ERR_UNSUPPORTED;
+    if (nens <= 128) rc = dg_run<T, 4, true>(a, *pl, st);
+    else if (nens <= 256) rc = dg_run<T, 8, true>(a, *pl, st);
+    cudaEventRecord(pl->used, st);
+    pl->was_used = true;
+    return rc;
+}
+
+extern "C" int exb_obs_solve_dist_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
+                                      const uint8_t *ob_assim, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                                      double *rec, unsigned long long *counters, int rank, int world, void *const *P_peers,
+                                      void *const *S_peers, void *stream) {
+    return dg_solve_dist<double>(plan, Ym, Yp, ob_value, ob_error, ob_assim, obgeo, nobs, nens, loc_mode, rec, counters, rank,
+                                 world, P_peers, S_peers, (cudaStream_t)stream);
+}
+extern "C" int exb_obs_solve_dist_f32(void *plan, float *Ym, float *Yp, const double *ob_value, const double *ob_error,
+                                      const uint8_t *ob_assim, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                                      double *rec, unsigned long long *counters, int rank, int world, void *const *P_peers,
+                                      void *const *S_peers, void *stream) {
+    return dg_solve_dist<float>(plan, Ym, Yp, ob_value, ob_error, ob_assim, obgeo, nobs, nens, loc_mode, rec, counters, rank,
+                                world, P_peers, S_peers, (cudaStream_t)stream);
+}
+
 extern "C" int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, void *stream,
                                    void **plan) {
     EXB_REQUIRE(obgeo && ob_assim && plan && nobs > 0, "null pointer or nobs <= 0");
     ExbObsPlan *pl = nullptr;
     const int rc = dg_plan_begin(obgeo, ob_assim, nobs, loc_mode, (cudaStream_t)stream, &pl);
+    *plan = pl;
+    return rc;
+}
+
+// Plan of the rows j = rank + v * world only, for exb_obs_solve_dist_*.
+extern "C" int exb_obs_plan_create_dist(const double *obgeo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, int rank,
+                                        int world, void *stream, void **plan) {
+    EXB_REQUIRE(obgeo && ob_assim && plan && nobs > 0, "null pointer or nobs <= 0");
+    EXB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank / world");
+    ExbObsPlan *pl = nullptr;
+    const int rc = dg_plan_begin(obgeo, ob_assim, nobs, loc_mode, (cudaStream_t)stream, &pl, world, rank);
     *plan = pl;
     return rc;
 }

@@ -215,17 +215,22 @@ class ObsPlan:
     the current stream compute the ob priors: the constructor only enqueues the counting pass (exb_obs_plan_create),
     finish() sizes the lists and enqueues the fill pass (exb_obs_plan_finish)."""
 
-    def __init__(self, obs_dev, geo, nobs, loc_mode):
+    def __init__(self, obs_dev, geo, nobs, loc_mode, rank=0, world=1):
         torch = _torch()
         self.handle = C.c_void_p()
+        self.rank, self.world = rank, world
         self.stream = torch.cuda.Stream(device=geo.device)
         ready = obs_dev.get('_ready')
         if ready is not None:
             self.stream.wait_event(ready)
         else:
             self.stream.wait_stream(torch.cuda.current_stream())
-        _lib.call('exb_obs_plan_create', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode,
-                  C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
+        if world > 1:           # lists of this rank's rows only (distributed solve)
+            _lib.call('exb_obs_plan_create_dist', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode, rank,
+                      world, C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
+        else:
+            _lib.call('exb_obs_plan_create', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode,
+                      C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
 
     def finish(self):
         _lib.call('exb_obs_plan_finish', self.handle)
@@ -234,6 +239,86 @@ class ObsPlan:
         if self.handle:
             _lib.call('exb_obs_plan_destroy', self.handle)
             self.handle = C.c_void_p()
+
+
+_DIST_BUFFERS = {}
+
+
+def _dist_buffers(nobs, nens, dtype, device, group):
+    """Symmetric (peer-mapped) record buffers of the distributed obs-space solve, cached per shape: the tensors, the
+    rendezvous handles and ctypes arrays of the peers' pointers."""
+    torch = _torch()
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    mc = 4 if nens <= 128 else 8
+    key = (nobs, mc, dtype, str(device), id(group))
+    if key not in _DIST_BUFFERS:
+        g = group if group is not None else dist.group.WORLD
+        P = symm_mem.empty(nobs * 32 * mc, dtype=dtype, device=device)
+        S = symm_mem.empty(nobs * 2, dtype=torch.float64, device=device)
+        hP, hS = symm_mem.rendezvous(P, g), symm_mem.rendezvous(S, g)
+        world = dist.get_world_size(g)
+        pp = (C.c_void_p * 8)(*[C.c_void_p(int(hP.buffer_ptrs[q])) if q < world else None for q in range(8)])
+        sp = (C.c_void_p * 8)(*[C.c_void_p(int(hS.buffer_ptrs[q])) if q < world else None for q in range(8)])
+        _DIST_BUFFERS[key] = (P, S, hP, hS, pp, sp)
+    return _DIST_BUFFERS[key]
+
+
+def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan, group=None):
+    """Obs-space solve with the rows dealt round-robin to the ranks of `group` (one process per GPU of an NVLink
+    domain): every rank solves nobs/world rows and publishes their records into all ranks' record buffers over peer
+    memory (exb_obs_solve_dist_*); afterwards ye rows, means, records and the pair counter are summed over the group
+    so that every rank holds the complete result, as after the replicated solve.  Returns False (nothing done) when
+    the plan is dense / multi-block or symmetric memory is unavailable."""
+    torch = _torch()
+    import torch.distributed as dist
+    g = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(g), dist.get_rank(g)
+    nobs = Ym.shape[0]
+    try:
+        P, S, hP, hS, pp, sp = _dist_buffers(nobs, nens, Yp.dtype, Yp.device, group)
+    except Exception as e:             # no peer access / symmetric memory in this build
+        import warnings
+        warnings.warn('distributed obs-space solve unavailable (%s); using the replicated one' % (e,))
+        return False
+    P.view(torch.uint8).fill_(255)
+    S.view(torch.uint8).fill_(255)
+    flag = torch.zeros(1, dtype=torch.int32, device=Yp.device)
+    dist.all_reduce(flag, group=g)     # stream-ordered barrier: every rank's sentinel fill precedes every kernel
+    rec.zero_()
+    c0 = counters[0:1].clone()
+    counters[0:1].zero_()
+    lib = _lib.load()
+    rc = getattr(lib, 'exb_obs_solve_dist_' + sfx)(
+        plan.handle, _lib.ptr(Ym), _lib.ptr(Yp), _lib.ptr(obs_dev['value']), _lib.ptr(obs_dev['error']),
+        _lib.ptr(obs_dev['assimilate']), _lib.ptr(geo), nobs, nens, loc_mode, _lib.ptr(rec), _lib.ptr(counters), rank, world,
+        pp, sp, _lib.stream_ptr())
+    if rc == -3:                       # EXB_ERR_UNSUPPORTED: identical decision on every rank (same plan)
+        counters[0:1].copy_(c0)
+        return False
+    if rc != 0:
+        raise _lib.ExbError('exb_obs_solve_dist_%s failed (%d): %s' % (sfx, rc, lib.exb_last_error().decode('utf-8', 'replace')))
+    mine = (torch.arange(nobs, device=Yp.device) % world) == rank
+    Yp.mul_(mine[:, None].to(Yp.dtype))
+    Ym.mul_(mine.to(Ym.dtype))
+    # NaN marks "not assimilated" in the records (post mean / variance): keep it out of the sum
+    nanmask = torch.isnan(rec)
+    rec.masked_fill_(nanmask, 0.0)
+    skipped = nanmask.to(rec.dtype)
+    for t in (Yp, Ym, rec, skipped, counters[0:1]):
+        dist.all_reduce(t, group=g)
+    rec.masked_fill_(skipped > 0, float('nan'))
+    counters[0:1].add_(c0)
+    return True
+
+
+def obs_dist_wanted(group):
+    """Multi-GPU runs over NCCL distribute the obs-space solve over the ranks (EXB_OBS_DIST=0: replicate it)."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get('EXB_OBS_DIST', '1') != '1' or not dist.is_initialized():
+        return False
+    return dist.get_world_size(group) > 1 and dist.get_backend(group) == 'nccl'
 
 
 def obs_plan_wanted(loc_mode):
@@ -322,7 +407,13 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         obs_dev, geo = obs_device if obs_device is not None else upload_obs(obs, dev, loc_mode)
         # predecessor lists of the obs-space solve: geometry only, started on a side stream now so that they are built
         # while the host and this stream work on the ob priors
-        plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode) if obs_plan_wanted(loc_mode) else None
+        plan = None
+        dist_solve = band is not None and obs_plan_wanted(loc_mode) and obs_dist_wanted(group)
+        if dist_solve:
+            import torch.distributed as dist
+            plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode, dist.get_rank(group), dist.get_world_size(group))
+        elif obs_plan_wanted(loc_mode):
+            plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
         if Y is None:
             Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group)
         elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
@@ -340,7 +431,15 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         tm.mark('setup')
         rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
         counters = torch.zeros(2, dtype=torch.int64, device=dev)
-        obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
+        done = False
+        if dist_solve:
+            done = obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan, group=group)
+            if not done:            # dense graph or no peer memory: replicated solve with a full plan
+                plan.destroy()
+                plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
+                plan.finish()
+        if not done:
+            obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
         tm.mark('obs_solve')
         grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
         if fused:

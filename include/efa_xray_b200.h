@@ -150,6 +150,8 @@ int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, const double
  * loc_mode) it was built from. */
 int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assimilate, int64_t nobs, int loc_mode, void *stream,
                         void **plan);
+int exb_obs_plan_create_dist(const double *obgeo, const uint8_t *ob_assimilate, int64_t nobs, int loc_mode, int rank,
+                             int world, void *stream, void **plan);   /* lists of the rows rank + v*world only */
 int exb_obs_plan_finish(void *plan);
 int exb_obs_plan_destroy(void *plan);
 int exb_obs_solve_planned_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
@@ -158,6 +160,23 @@ int exb_obs_solve_planned_f64(void *plan, double *Ym, double *Yp, const double *
 int exb_obs_solve_planned_f32(void *plan, float *Ym, float *Yp, const double *ob_value, const double *ob_error,
                               const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
                               int loc_mode, double *rec, unsigned long long *counters, void *stream);
+
+/* Obs-space solve distributed over the GPUs of one NVLink domain (<= 8): rank `rank` solves the obs rows j with
+ * j % world == rank and publishes their records into the record buffers of EVERY rank over peer memory, so that the
+ * dependency waits of all ranks resolve locally; the serial chain (longest dependency path) is unchanged, the work per
+ * GPU is 1/world.  P_peers[q] / S_peers[q] are pointers, valid on this device, to rank q's buffers (e.g. torch symmetric
+ * memory): P nobs*32*MC elements of T (MC = 4 up to 128 members, 8 above), S nobs*2 doubles.  Preconditions: every
+ * buffer is filled with 0xFF bytes and the group has synchronised after that; every rank passes identical inputs and
+ * its own plan from exb_obs_plan_create_dist (lists must fit one block).  Outputs (Ym, Yp, rec, counters[0]) are written for the rank's own rows
+ * only: zero the others and sum over the group.  Returns EXB_ERR_UNSUPPORTED when the plan is dense or multi-block. */
+int exb_obs_solve_dist_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
+                           const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                           double *rec, unsigned long long *counters, int rank, int world, void *const *P_peers,
+                           void *const *S_peers, void *stream);
+int exb_obs_solve_dist_f32(void *plan, float *Ym, float *Yp, const double *ob_value, const double *ob_error,
+                           const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens, int loc_mode,
+                           double *rec, unsigned long long *counters, int rank, int world, void *const *P_peers,
+                           void *const *S_peers, void *stream);
 
 /* exb_obs_solve_* only enqueues its kernels (the dependency-driven variant synchronises the stream once, to size
  * its work lists, before the solve itself is launched).  Its kernels wait on each other inside the launch; a
