@@ -50,6 +50,9 @@ CASES = {
                      frac_skip=0.05), 'GC', None),
     'gc_inflate': (dict(ny=19, nx=36, nmem=8, nvars=2, ntimes=1, nobs=30, cutoff_km=5000.0, seed=4),
                    'GC', 1.5),
+    # more obs than one panel / batch, many overlapping supports, mixed radii and errors, skipped obs
+    'gc_dense300': (dict(ny=37, nx=72, nmem=12, nvars=2, ntimes=1, nobs=300, cutoff_km=1500.0, seed=5,
+                         frac_skip=0.05, mixed_error=True, mixed_radius=True), 'GC', None),
 }
 
 
