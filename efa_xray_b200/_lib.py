@@ -22,6 +22,9 @@ SIGNATURES = {
     'exb_obs_prepare': [_p, _p, _p, _i64, _int, _p, _p],
     'exb_stencil_search': [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     'exb_stencil_search_rect': [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
+    'exb_pseudo_distance': [_p, _p, _i64, _dbl, _dbl, _p, _p],
+    'exb_stencil_combine': [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p],
+    'exb_pool_trim': [C.c_uint64],
     'exb_gather_f64': [_p, _i64, _int, _p, _p, _int, _i64, _p, _p],
     'exb_gather_f32': [_p, _i64, _int, _p, _p, _int, _i64, _p, _p],
     'exb_split_mean_pert_f64': [_p, _p, _i64, _int, _p],
@@ -34,7 +37,7 @@ SIGNATURES = {
     'exb_obs_solve_f32': [_p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p],
     'exb_obs_solve_async_status': [],
     'exb_obs_plan_create': [_p, _p, _i64, _int, _p, _p],
-    'exb_obs_plan_create_dist': [_p, _p, _i64, _int, _int, _int, _p, _p],
+    'exb_obs_plan_create_dist': [_p, _p, _i64, _int, _int, _int, _int, _p, _p],
     'exb_obs_plan_finish': [_p],
     'exb_obs_solve_dist_f64': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _int, _int, _p, _p, _p],
     'exb_obs_solve_dist_f32': [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _int, _int, _p, _p, _p],

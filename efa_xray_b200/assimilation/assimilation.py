@@ -21,8 +21,9 @@ class Assimilation():
     """Computes obs priors and formats the state for the update (assimilation.py:10-171)."""
 
     def __init__(self, state, obs, nproc=1, inflation=None, verbose=False):
-        """inflation: None, a float (all variables), or a dict of {variable name: float}
-        (assimilation.py:19-26; the file-name and per-dimension forms need xarray/netCDF and are not ported).
+        """inflation: None, a float (all variables), or a dict of {variable name: float} and/or
+        {'validtime' | 'y' | 'x' (| 'lat' | 'lon' when 1-D): array along that dimension}
+        (assimilation.py:19-26; the netCDF file-name form needs xarray and is not ported).
         nproc is accepted and ignored, as in the reference (assimilation.py:31)."""
         self.prior = state
         self.obs = obs
@@ -42,59 +43,97 @@ class Assimilation():
                          "defined by the reference (observation/observation.py:82)" % (loc,))
 
     def _obs_arrays(self, loc_mode):
-        """Structure-of-arrays view of self.obs with the forward-operator bookkeeping per ob."""
+        """Structure-of-arrays view of self.obs with the forward-operator bookkeeping per ob (one pass over the list
+        per attribute; everything after that is vectorised)."""
         st = self.prior
         obs = self.obs
         varnames = st.vars()
         nt, ny, nx = st.ntimes(), st.ny(), st.nx()
+        n = len(obs)
         vidx = {v: i for i, v in enumerate(varnames)}
         try:
-            var = np.array([vidx[ob.obtype] for ob in obs], dtype=np.int64)
+            var = np.fromiter((vidx[ob.obtype] for ob in obs), dtype=np.int64, count=n)
         except KeyError as e:
             raise KeyError('observation type %s is not a state variable %r' % (e, varnames))
-        times = np.array([np.datetime64(ob.time) for ob in obs]).astype('datetime64[ns]')
+        times = np.array([ob.time for ob in obs], dtype='datetime64[us]').astype('datetime64[ns]') if n else \
+            np.zeros(0, dtype='datetime64[ns]')
         tlo, thi, wlo, whi, outside = engine.time_weights(st['validtime'].values, times)
         if outside.any():
             print("Interpolation is outside of time range in state!")
             raise ObTimeOutsideState("observation %d (time %s) is outside the state's valid times"
                                      % (int(np.argmax(outside)), obs[int(np.argmax(outside))].time))
-        assim = np.array([1 if ob.assimilate_this else 0 for ob in obs], dtype=np.uint8)
-        hw = np.ones(len(obs))
+        assim = np.fromiter((1 if ob.assimilate_this else 0 for ob in obs), dtype=np.uint8, count=n)
+        hw = np.ones(n)
         if loc_mode == engine.LOC_GC:
-            for k, ob in enumerate(obs):
-                if ob.assimilate_this:
-                    hw[k] = abs(ob.localize_radius)      # TypeError on None, as observation.py:120
+            # abs(localize_radius) of the obs that will be assimilated: TypeError on None, as observation.py:120
+            radii = [ob.localize_radius if ob.assimilate_this else 1.0 for ob in obs]
+            if any(r is None for r in radii):
+                abs(None)                                # numpy would turn None into NaN silently
+            hw = np.abs(np.array(radii, dtype=np.float64))
         return engine.ObsArrays(
-            value=np.array([ob.value for ob in obs], dtype=np.float64),
-            error=np.array([ob.error for ob in obs], dtype=np.float64),
-            lat=np.array([ob.lat for ob in obs], dtype=np.float64),
-            lon=np.array([ob.lon for ob in obs], dtype=np.float64),
+            value=np.fromiter((ob.value for ob in obs), dtype=np.float64, count=n),
+            error=np.fromiter((ob.error for ob in obs), dtype=np.float64, count=n),
+            lat=np.fromiter((ob.lat for ob in obs), dtype=np.float64, count=n),
+            lon=np.fromiter((ob.lon for ob in obs), dtype=np.float64, count=n),
             halfwidth=hw, assimilate=assim,
             row0=(var * nt + tlo) * (ny * nx), row1=(var * nt + thi) * (ny * nx), tw0=wlo, tw1=whi)
 
-    def _inflation_factors(self):
-        """Per-level (variable x time) multiplicative factors, or None."""
-        if self.inflation is None:
+    _DIM_KEYS = ['validtime', 'lat', 'lon', 'x', 'y']
+
+    def _inflation_factors(self, inflation=None):
+        """Multiplicative inflation factors, or None: shape (nvars*ntimes,) -- one per level, for a float or a
+        per-variable dict (assimilation.py:62-69, :101-114) -- or (nvars, ntimes, ny, nx) flattened to one factor per
+        state row when the dict has per-dimension arrays (assimilation.py:83-100: validtime / y / x, and lat / lon
+        when those are 1-D coordinates; the reference multiplies the perturbations by each array in turn, broadcast
+        along its dimension, so the factors multiply)."""
+        inflation = self.inflation if inflation is None else inflation
+        if inflation is None:
             return None
         st = self.prior
         varnames = st.vars()
         nt = st.ntimes()
         fac = np.ones((len(varnames), nt))
-        if isinstance(self.inflation, float):
-            fac[:] = self.inflation                                   # assimilation.py:62-69
-        elif isinstance(self.inflation, dict):
-            for k, v in self.inflation.items():                       # assimilation.py:82-114
-                if k in ['validtime', 'lat', 'lon', 'x', 'y']:
-                    raise NotImplementedError('per-dimension inflation arrays need xarray broadcasting and '
-                                              'are not ported (assimilation.py:83-100)')
+        field = None                                                   # [nt, ny, nx] per-dimension product
+        if isinstance(inflation, float):
+            fac[:] = inflation                                        # assimilation.py:62-69
+        elif isinstance(inflation, dict):
+            for k, v in inflation.items():                            # assimilation.py:82-114, in dict order
+                if k in self._DIM_KEYS:
+                    v = np.asarray(v, dtype=np.float64)
+                    coord = st.coords[k]
+                    assert v.ndim == 1 and v.shape[0] == len(coord)   # assimilation.py:87-88
+                    if len(coord.dims) != 1:
+                        # DataArray(v, [(k, 2-D coordinate values)]) cannot be built in the reference either
+                        raise ValueError('inflation along %r needs a 1-D %r coordinate (it has dims %r)'
+                                         % (k, k, coord.dims))
+                    if field is None:
+                        field = np.ones((nt, st.ny(), st.nx()))
+                    ax = ('validtime', 'y', 'x').index(coord.dims[0])
+                    shape = [1, 1, 1]
+                    shape[ax] = v.shape[0]
+                    field = field * v.reshape(shape)
+                    continue
                 assert isinstance(v, float)
                 if k not in varnames:
                     print("Unable to find variable {:s} to inflate.  Skipping...".format(k))
                     continue
-                fac[varnames.index(k), :] = v
+                fac[varnames.index(k), :] = fac[varnames.index(k), :] * v
         else:
             raise NotImplementedError('inflation from a netCDF file name needs xarray (assimilation.py:71-79)')
+        if field is not None:
+            return (fac[:, :, None, None] * field[None]).ravel()
         return fac.ravel()
+
+    def _host_matrix(self):
+        """[Nstate, Nens] host matrix of the prior in to_vect layout: the state's own block when it has one (no
+        copy; callers only read it or hand it to the device), else a stacked copy."""
+        st = self.prior
+        if hasattr(st, '_consolidate'):
+            st._consolidate()
+            blk = st._block_view()
+            if blk is not None:
+                return blk.reshape(st.nstate(), st.nmems())
+        return np.ascontiguousarray(st.to_vect())
 
     def _device(self):
         import torch
@@ -107,7 +146,7 @@ class Assimilation():
         import torch
         dev = self._device()
         obs = self._obs_arrays(engine.LOC_NONE)
-        X = torch.from_numpy(np.ascontiguousarray(self.prior.to_vect())).to(dev)
+        X = torch.from_numpy(self._host_matrix()).to(dev)
         grid = self.prior._grid_tables()
         Y, nex = engine.ob_priors(X, grid, obs, engine._sfx(X.dtype))
         self._check_exact(int(nex.item()))
@@ -123,21 +162,37 @@ class Assimilation():
                              '(state/ensemble.py:195-196); set efa_xray_b200.EXACT_MATCH_POLICY = "nearest" '
                              'to use the nearest point instead' % n_exact)
 
-    def inflate_state(self):
-        """Inflate self.prior in place about its ensemble mean (assimilation.py:52-118)."""
+    def _apply_inflation(self, fac):
         import ctypes as C
         import torch
+        dev = self._device()
+        X = torch.from_numpy(self._host_matrix()).to(dev)
+        sfx = engine._sfx(X.dtype)
+        _lib.call('exb_inflate_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], fac.ctypes.data_as(C.c_void_p), fac.shape[0],
+                  X.shape[0] // fac.shape[0], _lib.stream_ptr())
+        self.prior.from_vect(X.cpu().numpy())
+
+    def inflate_state(self):
+        """Inflate self.prior about its ensemble mean (assimilation.py:52-118).
+
+        As in the reference, a float and per-variable entries change the caller's state IN PLACE
+        (`variables[v][:] = ...`, :65, :113), while the first per-dimension entry REBINDS self.prior to a new state
+        (`self.prior = perts * infl + mean`, :96): the caller's object keeps what had been applied before it, and
+        everything from there on acts on the new one."""
         if self.is_inflated:
             print("State already inflated.  Skipping additional inflation.")
             return
-        fac = self._inflation_factors()
-        dev = self._device()
-        X = torch.from_numpy(np.ascontiguousarray(self.prior.to_vect())).to(dev)
-        nlev = fac.shape[0]
-        sfx = engine._sfx(X.dtype)
-        _lib.call('exb_inflate_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], fac.ctypes.data_as(C.c_void_p), nlev,
-                  X.shape[0] // nlev, _lib.stream_ptr())
-        self.prior.from_vect(X.cpu().numpy())
+        if isinstance(self.inflation, dict):
+            items = list(self.inflation.items())
+            first_dim = next((i for i, (k, _) in enumerate(items) if k in self._DIM_KEYS), len(items))
+            pre, post = dict(items[:first_dim]), dict(items[first_dim:])
+            if pre:
+                self._apply_inflation(self._inflation_factors(pre))
+            if post:
+                self.prior = deepcopy(self.prior)
+                self._apply_inflation(self._inflation_factors(post))
+        else:
+            self._apply_inflation(self._inflation_factors())
         self.is_inflated = True
 
     def format_prior_state(self):
@@ -151,7 +206,7 @@ class Assimilation():
         obmeans, obperts = self.compute_ob_priors()
         if self.verbose: print("Converting state to vector")
         dev = self._device()
-        X = torch.from_numpy(np.ascontiguousarray(self.prior.to_vect())).to(dev)
+        X = torch.from_numpy(self._host_matrix()).to(dev)
         xm = torch.empty(X.shape[0], dtype=X.dtype, device=dev)
         _lib.call('exb_split_mean_pert_' + engine._sfx(X.dtype), _lib.ptr(X), _lib.ptr(xm), X.shape[0], X.shape[1],
                   _lib.stream_ptr())

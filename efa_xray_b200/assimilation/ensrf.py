@@ -30,22 +30,35 @@ class EnSRF(Assimilation):
         if self.verbose: print("Beginning update sequence")
         loc_mode = self._loc_mode(self.loc)
         dev = self._device()
+
+        if self.inflation is not None and not self.is_inflated:
+            # the reference inflates the prior before anything else (assimilation.py:132-134): the caller's state in
+            # place, except that per-dimension arrays rebind self.prior to a new state (inflate_state)
+            if self.verbose: print("Inflating Prior State")
+            self.inflate_state()
         st = self.prior
         nlev = st.nvars() * st.ntimes()
 
-        if self.inflation is not None and not self.is_inflated:
-            # the reference inflates the caller's state in place before anything else (assimilation.py:132-134)
-            if self.verbose: print("Inflating Prior State")
-            self.inflate_state()
-
         if self.verbose: print("Computing observation priors")
         obs = self._obs_arrays(loc_mode)
-        host = np.array(st.to_vect(), order='C', copy=True)     # the prior itself stays untouched (ensrf.py:165)
         tdtype = {'f64': torch.float64, 'f32': torch.float32}[self.dtype]
         if self.verbose: print("Beginning observation loop")
-        # host buffer in, analysis written back into it (upload, sweep and download overlap band by band)
+        # The prior is read where it lies (the state's contiguous, page-locked block: no to_vect copy, and the prior
+        # itself stays untouched, assimilation.py:165) and the analysis is written into a fresh block that the
+        # posterior state adopts (no deepcopy of the data, no from_vect copy).  Upload, sweep and download overlap
+        # band by band inside engine.analysis_host.
+        st._consolidate()
+        prior_blk = st._block_view()
+        if prior_blk is not None:
+            from ..state.ensemble import BLOCK_POOL
+            host = prior_blk.reshape(st.nstate(), st.nmems())
+            out_blk, owner = BLOCK_POOL.alloc(prior_blk.shape, prior_blk.dtype)
+            out = out_blk.reshape(host.shape)
+        else:                                    # variables on different dims / dtypes: stacked copy
+            host = np.array(st.to_vect(), order='C', copy=True)
+            out_blk, owner, out = None, None, host
         res = engine.analysis_host(host, nlev, None, None, obs, loc_mode, device=dev, dtype=tdtype,
-                                   grid=st._grid_tables())
+                                   grid=st._grid_tables(), out=out)
         self._check_exact(res.n_exact)
         self.last_result = res
 
@@ -64,6 +77,9 @@ class EnSRF(Assimilation):
                 ob.assimilated = False
 
         if self.verbose: print("Formatting posterior")
-        post_state = deepcopy(self.prior)
-        post_state.from_vect(host)
+        if out_blk is not None:
+            post_state = st._new_with_block(out_blk, owner)
+        else:
+            post_state = deepcopy(self.prior)
+            post_state.from_vect(host)
         return post_state, self.obs

@@ -149,34 +149,161 @@ extern "C" int exb_measure_dmma_peak(double *tflops, void *stream) {
 // ------------------------------------------------------------------------------------------
 // whole analysis with host buffers
 // ------------------------------------------------------------------------------------------
-// 8-point stencil = 4 space points x 2 time levels, weights multiplied (state/ensemble.py:226-237)
-__global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *__restrict__ w4,
-                                const int64_t *__restrict__ row0, const int64_t *__restrict__ row1,
-                                const double *__restrict__ tw0, const double *__restrict__ tw1, int64_t nobs,
-                                int64_t *__restrict__ idx8, double *__restrict__ w8) {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= nobs) return;
-    for (int p = 0; p < 4; ++p) {
-        idx8[k * 8 + p] = row0[k] + idx4[k * 4 + p];
-        w8[k * 8 + p] = tw0[k] * w4[k * 4 + p];
-        idx8[k * 8 + 4 + p] = row1[k] + idx4[k * 4 + p];
-        w8[k * 8 + 4 + p] = tw1[k] * w4[k * 4 + p];
+// ------------------------------------------------------------------------------------------
+// library-owned resources: memory pool, mapped host words, watchdog slots, pinned staging buffers
+// ------------------------------------------------------------------------------------------
+#include <mutex>
+#include <cstdlib>
+namespace {
+std::mutex g_res_mutex;
+cudaMemPool_t g_pool[64];
+bool g_pool_ready[64];
+}   // namespace
+
+static cudaError_t exb_pool_get(cudaMemPool_t *pool) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    if (!g_pool_ready[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        e = cudaMemPoolCreate(&g_pool[dev], &props);
+        if (e != cudaSuccess) return e;
+        // keep freed blocks cached (a 2.5 GB state buffer or a 0.5 GB list costs 20-100 ms to re-allocate on every
+        // analysis otherwise), but only up to a bound, and only in this library's own pool
+        double keep_gb = 32.0;
+        if (const char *env = getenv("EXB_POOL_KEEP_GB")) keep_gb = atof(env);
+        uint64_t keep = keep_gb <= 0.0 ? 0 : (uint64_t)(keep_gb * 1073741824.0);
+        e = cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        g_pool_ready[dev] = true;
     }
+    *pool = g_pool[dev];
+    return cudaSuccess;
 }
 
-// Stream-ordered work buffers from the default memory pool, which is told to keep freed blocks (a 2.5 GB state
-// buffer costs ~100 ms to cudaMalloc/cudaFree on every call otherwise).
-int exb_pool_setup() {
-    static bool done = false;
-    if (done) return EXB_OK;
-    int dev = 0;
+cudaError_t exb_malloc_async(void **p, size_t bytes, cudaStream_t st) {
     cudaMemPool_t pool;
-    EXB_CUDA(cudaGetDevice(&dev));
-    EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;
-    EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    done = true;
+    cudaError_t e = exb_pool_get(&pool);
+    if (e != cudaSuccess) return e;
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, st);
+}
+
+// Returns cached, currently unused blocks of the library's pool on the current device to the driver, keeping at most
+// keep_bytes.
+extern "C" int exb_pool_trim(uint64_t keep_bytes) {
+    cudaMemPool_t pool;
+    EXB_CUDA(exb_pool_get(&pool));
+    EXB_CUDA(cudaMemPoolTrimTo(pool, (size_t)keep_bytes));
     return EXB_OK;
+}
+
+namespace {
+constexpr int kWordSlots = 64, kStatusSlots = 1024;
+long long *g_words_host = nullptr;        // [kWordSlots][8], portable + mapped
+bool g_words_busy[kWordSlots];
+int *g_status_host = nullptr;             // [kStatusSlots]
+unsigned g_status_next = 0;
+thread_local int g_status_last = -1;
+struct PinnedBuf { void *p; size_t bytes; bool busy; };
+std::vector<PinnedBuf> g_pinned;
+
+int host_tables_init() {      // caller holds g_res_mutex
+    if (!g_words_host) {
+        EXB_CUDA(cudaHostAlloc(&g_words_host, sizeof(long long) * 8 * kWordSlots, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(g_words_host, 0, sizeof(long long) * 8 * kWordSlots);
+    }
+    if (!g_status_host) {
+        EXB_CUDA(cudaHostAlloc(&g_status_host, sizeof(int) * kStatusSlots, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(g_status_host, 0, sizeof(int) * kStatusSlots);
+    }
+    return EXB_OK;
+}
+}   // namespace
+
+int exb_host_words_acquire(ExbHostWords *w) {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    const int rc = host_tables_init();
+    if (rc != EXB_OK) return rc;
+    for (int i = 0; i < kWordSlots; ++i)
+        if (!g_words_busy[i]) {
+            g_words_busy[i] = true;
+            w->slot = i;
+            w->host = g_words_host + 8 * i;
+            void *d = nullptr;
+            EXB_CUDA(cudaHostGetDevicePointer(&d, g_words_host + 8 * i, 0));
+            w->dev = static_cast<long long *>(d);
+            return EXB_OK;
+        }
+    exb_set_error("exb_host_words_acquire: more than %d calls in flight", kWordSlots);
+    return EXB_ERR_UNSUPPORTED;
+}
+
+void exb_host_words_release(const ExbHostWords &w) {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    if (w.slot >= 0 && w.slot < kWordSlots) g_words_busy[w.slot] = false;
+}
+
+int exb_status_slot_next(int **host, int **dev) {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    const int rc = host_tables_init();
+    if (rc != EXB_OK) return rc;
+    const int i = (int)(g_status_next++ % kStatusSlots);
+    void *d = nullptr;
+    EXB_CUDA(cudaHostGetDevicePointer(&d, g_status_host + i, 0));
+    *host = g_status_host + i;
+    *dev = static_cast<int *>(d);
+    g_status_last = i;
+    return EXB_OK;
+}
+
+const int *exb_status_slot_last_dev() {
+    if (g_status_last < 0 || !g_status_host) return nullptr;
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, g_status_host + g_status_last, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return static_cast<const int *>(d);
+}
+
+// Verdict of the watchdog of the last exb_obs_solve_* issued by THIS host thread (call after synchronising its
+// stream): 0 ok, EXB_ERR_CUDA = a dependency wait never completed and the records are invalid.
+extern "C" int exb_obs_solve_async_status(void) {
+    if (g_status_last < 0 || !g_status_host) return EXB_OK;
+    const int v = *reinterpret_cast<volatile int *>(g_status_host + g_status_last);
+    if (v == 0) return EXB_OK;
+    exb_set_error("exb_obs_solve: a dependency wait never completed (watchdog, record %d); the obs-space records are invalid",
+                  v - 1);
+    return EXB_ERR_CUDA;
+}
+
+int exb_pinned_acquire(size_t bytes, void **p) {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    int best = -1;
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+        if (!g_pinned[i].busy && g_pinned[i].bytes >= bytes && (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes)) best = (int)i;
+    if (best < 0) {
+        // replace an idle buffer that is too small rather than growing the cache without bound
+        for (size_t i = 0; i < g_pinned.size(); ++i)
+            if (!g_pinned[i].busy) { cudaFreeHost(g_pinned[i].p); g_pinned.erase(g_pinned.begin() + i); break; }
+        PinnedBuf b{nullptr, bytes, false};
+        EXB_CUDA(cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocPortable));
+        g_pinned.push_back(b);
+        best = (int)g_pinned.size() - 1;
+    }
+    g_pinned[best].busy = true;
+    *p = g_pinned[best].p;
+    return EXB_OK;
+}
+
+void exb_pinned_release(void *p) {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    for (auto &b : g_pinned)
+        if (b.p == p) b.busy = false;
 }
 
 namespace {
@@ -185,7 +312,7 @@ struct DevBuf {
     cudaStream_t st = nullptr;
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
     template <typename T> T *as() { return static_cast<T *>(p); }
-    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return exb_malloc_async(&p, bytes, s); }
 };
 }   // namespace
 
@@ -219,7 +346,6 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nens >= 2 && nobs > 0, "bad sizes");
     EXB_REQUIRE(loc_mode != EXB_LOC_GC || ob_halfwidth_km, "loc_mode GC needs halfwidths");
     EXB_TRY(exb_device_check());
-    EXB_TRY(exb_pool_setup());
     const int64_t npts = ny * nx, nrows = nlev * npts;
     const size_t row_bytes = (size_t)nens * sizeof(double);
     cudaStream_t st = nullptr, s_in = nullptr, s_out = nullptr;
@@ -307,12 +433,9 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
         EXB_TRY(exb_stencil_search(dsl.as<double>(), dcl.as<double>(), dlat.as<double>(), dlon.as<double>(), npts,
                                    ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs, didx4.as<int64_t>(),
                                    dw4.as<double>(), dnex.as<int32_t>(), st));
-    stencil8_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(didx4.as<int64_t>(), dw4.as<double>(),
-                                                                     drow.as<int64_t>(), drow.as<int64_t>() + nobs,
-                                                                     dtw.as<double>(), dtw.as<double>() + nobs, nobs,
-                                                                     didx8.as<int64_t>(), dw8.as<double>());
-    exb_count_launches(1);
-    EXB_TRY(exb_check_launch("stencil8_kernel"));
+    EXB_TRY(exb_stencil_combine(didx4.as<int64_t>(), dw4.as<double>(), drow.as<int64_t>(), drow.as<int64_t>() + nobs,
+                                dtw.as<double>(), dtw.as<double>() + nobs, nobs, ny, nx, 0, ny, didx8.as<int64_t>(),
+                                dw8.as<double>(), st));
 
     // ---- band schedule ----------------------------------------------------------------------------------
     const bool fused = nens <= 103;

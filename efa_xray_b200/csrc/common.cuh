@@ -31,6 +31,26 @@ void exb_set_error(const char *fmt, ...);
 int exb_check_launch(const char *what);
 void exb_count_launches(int64_t n);   // bookkeeping for exb_launch_count()
 
+// Stream-ordered work buffers come from a memory pool OWNED by this library (one per device), not from the device's
+// default pool: freed blocks stay cached up to EXB_POOL_KEEP_GB (default 32 GiB; exb_pool_trim releases them) without
+// changing the behaviour of anybody else's cudaMallocAsync.  Free with cudaFreeAsync.
+cudaError_t exb_malloc_async(void **p, size_t bytes, cudaStream_t st);
+template <typename U> static inline cudaError_t exb_malloc_async(U **p, size_t bytes, cudaStream_t st) {
+    return exb_malloc_async(reinterpret_cast<void **>(p), bytes, st);
+}
+// Small page-locked, device-mapped words for results a kernel hands to the host without a copy (list totals,
+// watchdog verdicts).  Every call gets its own: nothing is shared between concurrent analyses.
+struct ExbHostWords { volatile long long *host; long long *dev; int slot; };      // 8 words
+int exb_host_words_acquire(ExbHostWords *w);
+void exb_host_words_release(const ExbHostWords &w);
+// Watchdog word of an obs-space solve: a fresh slot per solve (ring of 1024), remembered per host thread so that
+// exb_obs_solve_async_status() and the state sweep launched next from the same thread see THEIR solve's verdict.
+int exb_status_slot_next(int **host, int **dev);
+const int *exb_status_slot_last_dev();
+// Page-locked staging buffers (cached; cudaHostAlloc is too slow to do per call)
+int exb_pinned_acquire(size_t bytes, void **p);
+void exb_pinned_release(void *p);
+
 #define EXB_REQUIRE(cond, msg)                         \
     do {                                               \
         if (!(cond)) {                                 \

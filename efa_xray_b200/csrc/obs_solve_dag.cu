@@ -39,7 +39,9 @@
 #endif
 #define DG_SENT 0xFFFFFFFFFFFFFFFFull
 #define DG_FULL 0xffffffffu
-#define DG_WATCHDOG (1u << 24)  // polls (>= 100 ns each once backed off) before a wait is declared dead
+// A dependency wait is declared dead after this many seconds without progress (EXB_WATCHDOG_S overrides; a wait is
+// legitimately as long as everything that precedes the row, so the default also grows with nobs)
+#define DG_WATCHDOG_S 20.0
 
 template <typename T>
 int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_error, const uint8_t *ob_assim,
@@ -47,6 +49,14 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
                       unsigned long long *counters, cudaStream_t st, bool force, void *plan);
 
 __device__ __forceinline__ int64_t ceil_div64_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Rows of a distributed solve are dealt to the ranks in BLOCKS of `block` consecutive obs: rank r owns the obs j with
+// (j / block) % world == r; its v-th row is dg_row(v).  block = 1 is round-robin; world = 1 the identity.  The map is
+// strictly increasing in v, which is all the list builder and the ticket order need.
+struct DgDeal { int block, world, rank; };
+__host__ __device__ __forceinline__ int64_t dg_row(const DgDeal &d, int64_t v) {
+    return ((v / d.block) * d.world + d.rank) * (int64_t)d.block + v % d.block;
+}
 // ------------------------------------------------------------------------------------------
 // predecessor lists
 // ------------------------------------------------------------------------------------------
@@ -82,9 +92,9 @@ __global__ void dag_pack_kernel(const double *__restrict__ geo, const uint8_t *_
 template <bool FILL>
 __global__ void __launch_bounds__(DG_LWARPS * 32)
 dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_end, int *__restrict__ cnt,
-                const int64_t *__restrict__ off, int64_t list_base, int *__restrict__ list, int stride, int first) {
-    // [row_begin, row_end) are indices v into the rows this process solves: ob index j = first + v * stride
-    // (stride 1, first 0: all rows; the distributed solve builds the lists of its own rows only).  cnt / off / the
+                const int64_t *__restrict__ off, int64_t list_base, int *__restrict__ list, const DgDeal deal) {
+    // [row_begin, row_end) are indices v into the rows this process solves: ob index j = dg_row(deal, v)
+    // (world 1: all rows; the distributed solve builds the lists of its own rows only).  cnt / off / the
     // list segments are indexed by v.
     __shared__ float4 tile[DG_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,10 +105,10 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
     if (half == 1 && blk <= (int64_t)blockIdx.x) break;
     const int64_t v0 = row_begin + blk * DG_LROWS;
     const int64_t vw = v0 + warp * 32, v = vw + lane;
-    const int64_t jw = first + vw * stride;                           // first row of this warp
-    const int64_t j = first + v * stride;
+    const int64_t jw = dg_row(deal, vw);                              // first row of this warp
+    const int64_t j = dg_row(deal, v);
     const bool valid = v < row_end;
-    const int64_t jtop = first + ((v0 + DG_LROWS < row_end ? v0 + DG_LROWS : row_end) - 1) * stride;    // last row of this CTA
+    const int64_t jtop = dg_row(deal, (v0 + DG_LROWS < row_end ? v0 + DG_LROWS : row_end) - 1);         // last row of this CTA
     const float qnan = __int_as_float(0x7fc00000);                    // rows past the end: every test is false
     float4 me = make_float4(qnan, qnan, qnan, 0.f);
     if (valid) me = pk[j];
@@ -126,7 +136,7 @@ dag_list_kernel(const float4 *__restrict__ pk, int64_t row_begin, int64_t row_en
             }
         }
         // the warp's own 32 rows: k < j per lane
-        const int64_t last = jw + 31 * (int64_t)stride - t0;
+        const int64_t last = dg_row(deal, vw + 31) - t0;
         const int lim = last < DG_TILE ? (int)last : DG_TILE;
         for (int i = full; i < lim; ++i) {
             const float4 q = tile[i];
@@ -198,12 +208,14 @@ struct DgArgs {
     T *P;                        // published ye rows, stride 32*MC, sentinel-initialised
     double *S;                   // published scalars [nobs][2] = c1*innov, c1*beta; sentinel-initialised
     int *ticket;
-    int *status;                 // != 0: watchdog fired
+    int *status;                 // != 0: watchdog fired (value = 1 + index of the record that never arrived)
+    unsigned long long watchdog_ns;
     int64_t nobs, row_begin, row_end;
     int nens, loc_mode;
-    // distributed variant (DIST): rows j with j % world == rank are solved here; records are published into the P / S
+    // distributed variant (DIST): the rows dg_row(deal, t) are solved here; records are published into the P / S
     // buffers of every GPU of the group (peer memory over NVLink), readers always poll their own copy
     int world, rank;
+    DgDeal deal;
     void *P_peer[8];
     void *S_peer[8];
 };
@@ -343,9 +355,15 @@ __device__ __forceinline__ bool dg_ready(const DgRec<DgCfg<T, MC>::NW> &r) {
 
 // Waits until the polled word of ob k's record has been written.  Returns false when the watchdog fired (here
 // or elsewhere).  Takes no reference to the caller's record so that it stays in registers.
-__device__ __noinline__ bool dg_wait(const double *S, int *status, int k, int lane) {
+__device__ __forceinline__ unsigned long long dg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ bool dg_wait(const double *S, int *status, unsigned long long watchdog_ns, int k, int lane) {
     const double *s = S + (int64_t)k * 2;
     unsigned polls = 0;
+    unsigned long long t0 = 0;
     while (true) {
         unsigned long long b0, b1;
         dg_ld16(s, b0, b1);
@@ -353,9 +371,12 @@ __device__ __noinline__ bool dg_wait(const double *S, int *status, int k, int la
         ++polls;
         if (polls > 1) __nanosleep(polls < 8 ? 50 : (polls < 32 ? 200 : 500));
         if ((polls & 1023u) == 0) {
+            // wall-clock watchdog (the poll count says little on a time-sliced or preempted GPU)
             if (*reinterpret_cast<volatile int *>(status) != 0) return false;
-            if (polls >= DG_WATCHDOG) {
-                if (lane == 0) atomicExch(status, 1);
+            const unsigned long long now = dg_globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > watchdog_ns) {
+                if (lane == 0) atomicCAS(status, 0, k + 1);
                 return false;
             }
         }
@@ -383,7 +404,7 @@ __device__ __forceinline__ bool dg_step(const DgArgs<T> &a, int lane, DgRow<T, M
     constexpr int NW = DgCfg<T, MC>::NW;
     constexpr int PER = DgWord<T>::PER;
     while (!dg_ready<T, MC>(cur)) {
-        if (!dg_wait(a.S, a.status, r.k, lane)) { r.dead = true; return false; }
+        if (!dg_wait(a.S, a.status, a.watchdog_ns, r.k, lane)) { r.dead = true; return false; }
         dg_fetch<T, MC>(a, r.k, lane, cur);
     }
     const bool more = r.m != 0;
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         if (lane == 0) t = atomicAdd(a.ticket, 1);
         t = __shfl_sync(DG_FULL, t, 0);
         int64_t j = a.row_begin + t;
-        if (DIST) j = a.rank + (int64_t)t * a.world;      // t-th row of this rank (row_begin is 0 when distributed)
+        if (DIST) j = dg_row(a.deal, t);                  // t-th row of this rank (row_begin is 0 when distributed)
         if (j >= a.row_end) break;
 
         // ---- this row: perturbations (lane owns members [MC*lane, MC*lane+MC)), mean, geometry ----
@@ -564,43 +585,32 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+static unsigned long long dg_watchdog_ns(int64_t nobs) {
+    double sec = DG_WATCHDOG_S + 1e-4 * (double)nobs;
+    if (const char *e = getenv("EXB_WATCHDOG_S")) { const double v = atof(e); if (v > 0.0) sec = v; }
+    return (unsigned long long)(sec * 1e9);
+}
+
 namespace {
 struct AsyncBuf {
     void *p = nullptr;
     cudaStream_t st;
     explicit AsyncBuf(cudaStream_t s) : st(s) {}
     ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    cudaError_t alloc(size_t bytes) { return exb_malloc_async(&p, bytes ? bytes : 1, st); }
     template <typename U> U *as() { return static_cast<U *>(p); }
 };
-int *g_status_host = nullptr;     // pinned, mapped: the watchdog's verdict, readable without a device sync
-int *g_status_dev = nullptr;
 }   // namespace
-
-// Status of the asynchronous part of the last exb_obs_solve_* on this process: 0 ok, 1 = the dependency wait
-// watchdog fired (results are invalid).  Call after synchronising the stream.
-extern "C" int exb_obs_solve_async_status(void) {
-    if (!g_status_host) return 0;
-    const int v = *reinterpret_cast<volatile int *>(g_status_host);
-    if (v == 0) return EXB_OK;
-    exb_set_error("exb_obs_solve: a dependency wait never completed (watchdog); the obs-space records are invalid");
-    return EXB_ERR_CUDA;
-}
 
 // ------------------------------------------------------------------------------------------
 // plan = everything that depends on the observation geometry only (predecessor lists).  It can be built on a side
 // stream while the ob priors are still being computed (exb_obs_plan_create) and is consumed by
 // exb_obs_solve_planned_*; exb_obs_solve_* builds a temporary one.
 // ------------------------------------------------------------------------------------------
-// Pinned staging buffer for the row offsets (reused; cudaHostAlloc is too slow to do per plan)
-static int64_t *g_off_pinned = nullptr;
-static size_t g_off_pinned_n = 0;
-static bool g_off_pinned_busy = false;
-
 struct ExbObsPlan {
     int64_t nobs = 0;
     int loc_mode = 0;
-    int stride = 1, first = 0;            // rows of this plan: first + v * stride (distributed solve: world, rank)
+    DgDeal deal{1, 1, 0};                 // rows of this plan: dg_row(deal, v) (distributed solve: blocks dealt to the ranks)
     int64_t nrows = 0;                    // number of those rows
     cudaStream_t st = nullptr;            // stream the plan was built on (its buffers are freed there)
     float4 *pk = nullptr;
@@ -611,27 +621,13 @@ struct ExbObsPlan {
     int64_t budget = 0;
     cudaEvent_t ready = nullptr, used = nullptr;
     bool was_used = false;
-    bool finished = false, uses_pinned = false;
+    bool finished = false;
+    int64_t *off_pinned = nullptr;        // page-locked staging buffer of the row offsets (exb_pinned_acquire)
 };
-
-static int dg_pool_setup() {
-    if (g_status_host) return EXB_OK;
-    // work buffers come from the stream-ordered pool; keep freed blocks cached instead of returning them to
-    // the driver at every synchronisation (a 0.5 GB list costs ~20 ms to re-allocate otherwise)
-    int dev = 0;
-    cudaMemPool_t pool;
-    EXB_CUDA(cudaGetDevice(&dev));
-    EXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;
-    EXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    EXB_CUDA(cudaHostAlloc(&g_status_host, sizeof(int), cudaHostAllocMapped));
-    EXB_CUDA(cudaHostGetDevicePointer(&g_status_dev, g_status_host, 0));
-    return EXB_OK;
-}
 
 static void dg_plan_free(ExbObsPlan *pl) {
     if (!pl) return;
-    if (pl->uses_pinned) { cudaStreamSynchronize(pl->st); g_off_pinned_busy = false; }
+    if (pl->off_pinned) { cudaStreamSynchronize(pl->st); exb_pinned_release(pl->off_pinned); pl->off_pinned = nullptr; }
     if (pl->was_used && pl->used) cudaStreamWaitEvent(pl->st, pl->used, 0);
     if (pl->pk) cudaFreeAsync(pl->pk, pl->st);
     if (pl->off) cudaFreeAsync(pl->off, pl->st);
@@ -643,45 +639,39 @@ static void dg_plan_free(ExbObsPlan *pl) {
 
 // Step 1 (asynchronous): enqueues packing, the count pass, the prefix sum and the download of the row offsets on st.
 static int dg_plan_begin(const double *geo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, cudaStream_t st, ExbObsPlan **out,
-                         int stride = 1, int first = 0) {
+                         DgDeal deal = DgDeal{1, 1, 0}) {
     *out = nullptr;
     if (nobs >= 0x7fffffff) return EXB_ERR_UNSUPPORTED;
-    const int rc0 = dg_pool_setup();
-    if (rc0 != EXB_OK) return rc0;
     ExbObsPlan *pl = new ExbObsPlan();
     pl->nobs = nobs; pl->loc_mode = loc_mode; pl->st = st;
-    pl->stride = stride; pl->first = first;
-    pl->nrows = first < nobs ? (nobs - first + stride - 1) / stride : 0;
+    pl->deal = deal;
+    {
+        const int64_t cyc = (int64_t)deal.block * deal.world, rem = nobs % cyc - (int64_t)deal.rank * deal.block;
+        pl->nrows = (nobs / cyc) * deal.block + (rem < 0 ? 0 : (rem > deal.block ? deal.block : rem));
+    }
     const int64_t nrows = pl->nrows > 0 ? pl->nrows : 1;
     struct Guard { ExbObsPlan *p; ~Guard() { if (p) dg_plan_free(p); } } guard{pl};
     int *cnt = nullptr;
     EXB_CUDA(cudaEventCreateWithFlags(&pl->ready, cudaEventDisableTiming));
     EXB_CUDA(cudaEventCreateWithFlags(&pl->used, cudaEventDisableTiming));
-    EXB_CUDA(cudaMallocAsync(&pl->pk, (size_t)nobs * sizeof(float4), st));
-    EXB_CUDA(cudaMallocAsync(&pl->off, (size_t)(nrows + 1) * sizeof(int64_t), st));
-    EXB_CUDA(cudaMallocAsync(&cnt, (size_t)nrows * sizeof(int), st));
+    EXB_CUDA(exb_malloc_async(&pl->pk, (size_t)nobs * sizeof(float4), st));
+    EXB_CUDA(exb_malloc_async(&pl->off, (size_t)(nrows + 1) * sizeof(int64_t), st));
+    EXB_CUDA(exb_malloc_async(&cnt, (size_t)nrows * sizeof(int), st));
     dag_pack_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(geo, ob_assim, nobs, loc_mode, pl->pk);
     EXB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nrows * sizeof(int), st));
     dag_list_kernel<false><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-        pl->pk, 0, pl->nrows, cnt, nullptr, 0, nullptr, stride, first);
+        pl->pk, 0, pl->nrows, cnt, nullptr, 0, nullptr, deal);
     dag_scan_kernel<<<1, 1024, 0, st>>>(cnt, nrows, pl->off);
     exb_count_launches(3);
     cudaFreeAsync(cnt, st);
     EXB_CUDA(cudaGetLastError());
     pl->off_h.resize((size_t)nrows + 1);
-    if (!g_off_pinned_busy) {
-        if (g_off_pinned_n < (size_t)nobs + 1) {
-            if (g_off_pinned) cudaFreeHost(g_off_pinned);
-            g_off_pinned = nullptr;
-            g_off_pinned_n = 0;
-            EXB_CUDA(cudaHostAlloc(&g_off_pinned, ((size_t)nobs + 1) * sizeof(int64_t), cudaHostAllocDefault));
-            g_off_pinned_n = (size_t)nobs + 1;
-        }
-        pl->uses_pinned = true;
-        g_off_pinned_busy = true;
-        EXB_CUDA(cudaMemcpyAsync(g_off_pinned, pl->off, (size_t)(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    } else {
-        EXB_CUDA(cudaMemcpyAsync(pl->off_h.data(), pl->off, (size_t)(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    {
+        void *hp = nullptr;
+        const int rcp = exb_pinned_acquire((size_t)(nrows + 1) * sizeof(int64_t), &hp);
+        if (rcp != EXB_OK) return rcp;
+        pl->off_pinned = static_cast<int64_t *>(hp);
+        EXB_CUDA(cudaMemcpyAsync(pl->off_pinned, pl->off, (size_t)(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
     guard.p = nullptr;
     *out = pl;
@@ -694,13 +684,13 @@ static int dg_plan_finish(ExbObsPlan *pl) {
     const int64_t nobs = pl->nobs, nrows = pl->nrows > 0 ? pl->nrows : 1;
     cudaStream_t st = pl->st;
     EXB_CUDA(cudaStreamSynchronize(st));
-    if (pl->uses_pinned) {
-        memcpy(pl->off_h.data(), g_off_pinned, ((size_t)nrows + 1) * sizeof(int64_t));
-        g_off_pinned_busy = false;
-        pl->uses_pinned = false;
+    if (pl->off_pinned) {
+        memcpy(pl->off_h.data(), pl->off_pinned, ((size_t)nrows + 1) * sizeof(int64_t));
+        exb_pinned_release(pl->off_pinned);
+        pl->off_pinned = nullptr;
     }
     const int64_t total = pl->off_h[(size_t)nrows];
-    const double dense = 0.5 * (double)nobs * (double)(nobs - 1) / (double)pl->stride;
+    const double dense = 0.5 * (double)nobs * (double)(nobs - 1) / (double)pl->deal.world;
     pl->dense = nobs > 2048 && (double)total > 0.5 * dense;
     pl->budget = (int64_t)1 << 30;                                      // list entries per row block (4 GiB)
     if (const char *e = getenv("EXB_DAG_BUDGET")) {
@@ -708,9 +698,9 @@ static int dg_plan_finish(ExbObsPlan *pl) {
         if (v > 0) pl->budget = v;
     }
     if (!pl->dense && total > 0 && total <= pl->budget) {
-        EXB_CUDA(cudaMallocAsync(&pl->list, (size_t)total * sizeof(int), st));
+        EXB_CUDA(exb_malloc_async(&pl->list, (size_t)total * sizeof(int), st));
         dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-            pl->pk, 0, pl->nrows, nullptr, pl->off, 0, pl->list, pl->stride, pl->first);
+            pl->pk, 0, pl->nrows, nullptr, pl->off, 0, pl->list, pl->deal);
         exb_count_launches(1);
         EXB_CUDA(cudaGetLastError());
     }
@@ -776,12 +766,12 @@ static int dg_run(DgArgs<T> a, const ExbObsPlan &pl, cudaStream_t st) {
         const int64_t nrows = b.second - b.first;
         if (!pl.list && !DIST && off_h[b.second] > off_h[b.first]) {
             dag_list_kernel<true><<<(unsigned)ceil_div64(ceil_div64(nrows, DG_LROWS), 2), DG_LWARPS * 32, 0, st>>>(
-                pl.pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>(), 1, 0);
+                pl.pk, b.first, b.second, nullptr, a.off, a.list_base, list.as<int>(), DgDeal{1, 1, 0});
             exb_count_launches(1);
         }
         EXB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(int), st));
         int64_t grid = (int64_t)sms * per_sm;
-        const int64_t need = ceil_div64(DIST ? ceil_div64(nrows, a.world) + 1 : nrows, DG_WARPS);
+        const int64_t need = ceil_div64(DIST ? pl.nrows + 1 : nrows, DG_WARPS);
         if (grid > need) grid = need;
         dag_solve_kernel<T, MC, DIST><<<(unsigned)grid, DG_WARPS * 32, 0, st>>>(a);
         exb_count_launches(1);
@@ -801,7 +791,7 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
         if (rc != EXB_OK) return rc;
         pl = tmp;
     } else {
-        if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->stride != 1) {
+        if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->deal.world != 1) {
             exb_set_error("exb_obs_solve: the plan was built for another observation set (or for a distributed solve)");
             return EXB_ERR_ARG;
         }
@@ -811,13 +801,20 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
     }
     struct TmpGuard { ExbObsPlan *p; ~TmpGuard() { if (p) dg_plan_free(p); } } tguard{tmp};
     if (!force && pl->dense) return EXB_ERR_UNSUPPORTED;
-    *g_status_host = 0;
     DgArgs<T> a;
+    {
+        int *sh = nullptr, *sd = nullptr;
+        const int rcs = exb_status_slot_next(&sh, &sd);
+        if (rcs != EXB_OK) return rcs;
+        EXB_CUDA(cudaMemsetAsync(sd, 0, sizeof(int), st));      // stream-ordered: an earlier solve's verdict is its own
+        a.status = sd;
+        a.watchdog_ns = dg_watchdog_ns(nobs);
+    }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
-    a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
+    a.ticket = nullptr; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
     a.loc_mode = loc_mode;
-    a.world = 1; a.rank = 0;
+    a.world = 1; a.rank = 0; a.deal = DgDeal{1, 1, 0};
     for (int q = 0; q < 8; ++q) { a.P_peer[q] = nullptr; a.S_peer[q] = nullptr; }
     int rc = EXB_ERR_UNSUPPORTED;
     if (nens <= 128) rc = dg_run<T, 4, false>(a, *pl, st);
@@ -845,7 +842,7 @@ static int dg_solve_dist(void *plan, T *Ym, T *Yp, const double *ob_value, const
     EXB_REQUIRE(plan && Ym && Yp && ob_value && ob_error && ob_assim && geo && rec && P_peers && S_peers, "null pointer");
     EXB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank / world");
     ExbObsPlan *pl = static_cast<ExbObsPlan *>(plan);
-    if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->stride != world || pl->first != rank) {
+    if (pl->nobs != nobs || pl->loc_mode != loc_mode || pl->deal.world != world || pl->deal.rank != rank) {
         exb_set_error("exb_obs_solve_dist: the plan was built for another observation set, rank or group size");
         return EXB_ERR_ARG;
     }
@@ -853,13 +850,20 @@ static int dg_solve_dist(void *plan, T *Ym, T *Yp, const double *ob_value, const
     if (rcf != EXB_OK) return rcf;
     if (pl->dense || (!pl->list && pl->off_h.back() > 0)) return EXB_ERR_UNSUPPORTED;
     EXB_CUDA(cudaStreamWaitEvent(st, pl->ready, 0));
-    *g_status_host = 0;
     DgArgs<T> a;
+    {
+        int *sh = nullptr, *sd = nullptr;
+        const int rcs = exb_status_slot_next(&sh, &sd);
+        if (rcs != EXB_OK) return rcs;
+        EXB_CUDA(cudaMemsetAsync(sd, 0, sizeof(int), st));      // stream-ordered: an earlier solve's verdict is its own
+        a.status = sd;
+        a.watchdog_ns = dg_watchdog_ns(nobs);
+    }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
-    a.ticket = nullptr; a.status = g_status_dev; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
+    a.ticket = nullptr; a.nobs = nobs; a.row_begin = 0; a.row_end = nobs; a.nens = nens;
     a.loc_mode = loc_mode;
-    a.world = world; a.rank = rank;
+    a.world = world; a.rank = rank; a.deal = pl->deal;
     for (int q = 0; q < 8; ++q) { a.P_peer[q] = q < world ? P_peers[q] : nullptr; a.S_peer[q] = q < world ? S_peers[q] : nullptr; }
     int rc = EXB_ERR_UNSUPPORTED;
     if (nens <= 128) rc = dg_run<T, 4, true>(a, *pl, st);
@@ -893,13 +897,14 @@ extern "C" int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assim,
     return rc;
 }
 
-// Plan of the rows j = rank + v * world only, for exb_obs_solve_dist_*.
+// Plan of this rank's rows only (blocks of `block` consecutive obs dealt round-robin to the ranks), for
+// exb_obs_solve_dist_*.
 extern "C" int exb_obs_plan_create_dist(const double *obgeo, const uint8_t *ob_assim, int64_t nobs, int loc_mode, int rank,
-                                        int world, void *stream, void **plan) {
+                                        int world, int block, void *stream, void **plan) {
     EXB_REQUIRE(obgeo && ob_assim && plan && nobs > 0, "null pointer or nobs <= 0");
-    EXB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank / world");
+    EXB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && block >= 1, "bad rank / world / block");
     ExbObsPlan *pl = nullptr;
-    const int rc = dg_plan_begin(obgeo, ob_assim, nobs, loc_mode, (cudaStream_t)stream, &pl, world, rank);
+    const int rc = dg_plan_begin(obgeo, ob_assim, nobs, loc_mode, (cudaStream_t)stream, &pl, DgDeal{block, world, rank});
     *plan = pl;
     return rc;
 }

@@ -373,7 +373,7 @@ static int ps_launch(PsArgs<T> &a, cudaStream_t st) {
     if ((a.npanels + (grid - 2)) / (grid - 1) > PS_MAXCHUNKS) return EXB_ERR_UNSUPPORTED;    // too many chunks per worker
     int *ctl = nullptr;
     const size_t ctl_bytes = sizeof(int) * (PS_CTL_PAD + (size_t)a.npanels + 1);
-    EXB_CUDA(cudaMallocAsync(&ctl, ctl_bytes, st));
+    EXB_CUDA(exb_malloc_async(&ctl, ctl_bytes, st));
     EXB_CUDA(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
     a.ctl = ctl;
     void *params[] = {(void *)&a};

@@ -188,6 +188,25 @@ nearest4_kernel(const double *__restrict__ sl_g, const double *__restrict__ cl_g
     }
 }
 
+// Squared pseudo-distance of ONE observation to every grid point, with the roundings of nearest4_kernel: the sort key
+// of nearest_points for any npt (state/ensemble.py:160-165; hypot is monotone in it).
+__global__ void pseudo_distance_kernel(const double *__restrict__ sl_g, const double *__restrict__ cl_g, int64_t npts,
+                                       double osl, double ocl, double *__restrict__ out) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const double a = sl_g[p] - osl, b = cl_g[p] - ocl;
+    out[p] = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+}
+
+extern "C" int exb_pseudo_distance(const double *sinlat_g, const double *coslon_g, int64_t npts, double ob_sinlat,
+                                   double ob_coslon, double *d2, void *stream) {
+    EXB_REQUIRE(sinlat_g && coslon_g && d2 && npts > 0, "null pointer or npts <= 0");
+    pseudo_distance_kernel<<<(unsigned)ceil_div64(npts, 256), 256, 0, (cudaStream_t)stream>>>(sinlat_g, coslon_g, npts,
+                                                                                                ob_sinlat, ob_coslon, d2);
+    exb_count_launches(1);
+    return exb_check_launch("pseudo_distance_kernel");
+}
+
 // Rectilinear grids (lat depends on y only, lon on x only -- every regular lat-lon grid): the squared
 // pseudo-distance separates, d2(y, x) = A[y] + B[x] with A = (sin lat_y - sin lat_ob)^2 and
 // B = (cos lon_x - cos lon_ob)^2, so the 4 smallest d2 are among the 8 smallest A x the 8 smallest B.
@@ -321,6 +340,40 @@ __global__ void gather_kernel(const T *__restrict__ X, int nens, const int64_t *
         }
         Y[k * nens + m] = (T)acc;
     }
+}
+
+// 8-point stencil = 4 space points x 2 time levels, weights multiplied (state/ensemble.py:226-237); with a latitude
+// band [y_begin, y_end) the row indices are re-based to a shard that holds only those grid rows of every level, and
+// stencil points outside the band get weight 0 (their partial sums belong to other ranks).
+__global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *__restrict__ w4,
+                                const int64_t *__restrict__ row0, const int64_t *__restrict__ row1,
+                                const double *__restrict__ tw0, const double *__restrict__ tw1, int64_t nobs,
+                                int64_t ny, int64_t nx, int64_t y_begin, int64_t y_end,
+                                int64_t *__restrict__ idx8, double *__restrict__ w8) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nobs) return;
+    const int64_t npts = ny * nx, nyl = y_end - y_begin;
+    for (int h = 0; h < 2; ++h) {
+        const int64_t lev = (h ? row1[k] : row0[k]) / npts;
+        const double tw = h ? tw1[k] : tw0[k];
+        for (int p = 0; p < 4; ++p) {
+            const int64_t pt = idx4[k * 4 + p], y = pt / nx, x = pt - y * nx;
+            const bool inside = y >= y_begin && y < y_end;
+            idx8[k * 8 + 4 * h + p] = inside ? (lev * nyl + (y - y_begin)) * nx + x : 0;
+            w8[k * 8 + 4 * h + p] = inside ? tw * w4[k * 4 + p] : 0.0;
+        }
+    }
+}
+
+extern "C" int exb_stencil_combine(const int64_t *idx4, const double *w4, const int64_t *row0, const int64_t *row1,
+                                   const double *tw0, const double *tw1, int64_t nobs, int64_t ny, int64_t nx,
+                                   int64_t y_begin, int64_t y_end, int64_t *idx8, double *w8, void *stream) {
+    EXB_REQUIRE(idx4 && w4 && row0 && row1 && tw0 && tw1 && idx8 && w8, "null pointer");
+    EXB_REQUIRE(nobs > 0 && ny > 0 && nx > 0 && y_begin >= 0 && y_end <= ny && y_begin < y_end, "bad sizes");
+    stencil8_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, (cudaStream_t)stream>>>(idx4, w4, row0, row1, tw0, tw1, nobs,
+                                                                                         ny, nx, y_begin, y_end, idx8, w8);
+    exb_count_launches(1);
+    return exb_check_launch("stencil8_kernel");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -504,7 +557,7 @@ static int inflate_impl(T *X, int64_t nrows, int nens, const double *factor_host
     EXB_REQUIRE(X && factor_host && nfactor > 0 && rows_per_factor > 0, "null pointer or bad factor layout");
     EXB_REQUIRE(nfactor * rows_per_factor >= nrows, "factors do not cover all rows");
     double *fdev = nullptr;
-    EXB_CUDA(cudaMallocAsync(&fdev, nfactor * sizeof(double), (cudaStream_t)stream));
+    EXB_CUDA(exb_malloc_async(&fdev, nfactor * sizeof(double), (cudaStream_t)stream));
     EXB_CUDA(cudaMemcpyAsync(fdev, factor_host, nfactor * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     int rc = row_impl<T, 1>(X, nullptr, nrows, nens, fdev, rows_per_factor, stream, "inflate");
     EXB_CUDA(cudaFreeAsync(fdev, (cudaStream_t)stream));

@@ -796,25 +796,24 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         p.nctx = (p.nx + ctx - 1) / ctx;
         const int cr0 = p.pr0 / SP_CT, cr1 = (pr1 + SP_CT - 1) / SP_CT;
         const int ntiles = (cr1 - cr0) * p.nctx;
-        EXB_CUDA(cudaMallocAsync(&caps, sizeof(float4) * ntiles, st));
-        EXB_CUDA(cudaMallocAsync(&cnt, sizeof(int) * ntiles, st));
-        EXB_CUDA(cudaMallocAsync(&off, sizeof(int64_t) * (ntiles + 1), st));
+        EXB_CUDA(exb_malloc_async(&caps, sizeof(float4) * ntiles, st));
+        EXB_CUDA(exb_malloc_async(&cnt, sizeof(int) * ntiles, st));
+        EXB_CUDA(exb_malloc_async(&off, sizeof(int64_t) * (ntiles + 1), st));
         const unsigned gridw = (unsigned)ceil_div64((int64_t)ntiles * 32, 256);
         sweep_tile_caps_kernel<<<gridw, 256, 0, st>>>(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, p.pr0, cty, ctx, p.nctx, ntiles, caps);
         sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, cnt, nullptr, nullptr);
-        static long long *total_host = nullptr, *total_dev = nullptr;
-        if (!total_host) {
-            EXB_CUDA(cudaHostAlloc(&total_host, 2 * sizeof(long long), cudaHostAllocMapped));
-            EXB_CUDA(cudaHostGetDevicePointer(&total_dev, total_host, 0));
-        }
-        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off, total_dev);
-        sweep_eq_row_kernel<<<1, 256, 0, st>>>(p.grid_u + 2 * p.npts, p.nx, p.y_begin, p.y_end, total_dev + 1);
+        ExbHostWords hw;                   // this call's own mapped words: [0] list total, [1] equator row
+        const int rcw = exb_host_words_acquire(&hw);
+        if (rcw != EXB_OK) return rcw;
+        struct WordsGuard { ExbHostWords w; ~WordsGuard() { exb_host_words_release(w); } } wguard{hw};
+        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off, hw.dev);
+        sweep_eq_row_kernel<<<1, 256, 0, st>>>(p.grid_u + 2 * p.npts, p.nx, p.y_begin, p.y_end, hw.dev + 1);
         exb_count_launches(4);
         EXB_CUDA(cudaStreamSynchronize(st));
-        const long long total = *reinterpret_cast<volatile long long *>(total_host);
-        p.eq_row = (int)*reinterpret_cast<volatile long long *>(total_host + 1);
+        const long long total = hw.host[0];
+        p.eq_row = (int)hw.host[1];
         p.pr_eq = p.eq_row / bty;
-        EXB_CUDA(cudaMallocAsync(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
+        EXB_CUDA(exb_malloc_async(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
         sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, nullptr, off, list);
         exb_count_launches(1);
         // the kernel indexes tiles by absolute coarse row: shift the offsets' base

@@ -348,7 +348,7 @@ static int state_update_impl(T *xm, T *Xp, int64_t nlev, int64_t ny, int64_t nx,
     if (ob_begin == ob_end) return EXB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     float4 *scan = nullptr;
-    EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
+    EXB_CUDA(exb_malloc_async(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
     exb_count_launches(1);
     {
@@ -415,7 +415,7 @@ static int state_sweep_impl(T *X, int64_t nlev, int64_t ny, int64_t nx, int nens
     if (ob_begin == ob_end || y_begin == y_end) return EXB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     float4 *scan = nullptr;
-    EXB_CUDA(cudaMallocAsync(&scan, (size_t)nobs * sizeof(float4), st));
+    EXB_CUDA(exb_malloc_async(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
     exb_count_launches(1);
     const int rc = exb_state_sweep_pipe<T>(nullptr, X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin,

@@ -49,6 +49,7 @@ class AnalysisResult:
     n_exact: int = 0             # obs within 1 km of a selected grid point
     state_pairs: int = 0         # sum_k |F_s(k)|   (state rows with non-zero weight, all levels)
     obs_pairs: int = 0           # sum_k |F_o(k)|
+    obs_solve: str = ''          # which obs-space solve ran: 'replicated' | 'distributed(block=b)' | 'single'
     ms: dict = field(default_factory=dict)
 
 
@@ -111,17 +112,21 @@ class GridTables:
                   _lib.stream_ptr())
 
 
-def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False):
+def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False, dev_tables=None):
     """4 nearest points (pseudo-metric) and inverse-distance weights for every ob -> device tensors
-    idx4 [nobs,4] int64, w4 [nobs,4] float64, and the number of obs within 1 km of a selected point."""
+    idx4 [nobs,4] int64, w4 [nobs,4] float64, and the number of obs within 1 km of a selected point.
+    dev_tables = (lat, lon, sin(lat), cos(lon)) already on the device (upload_obs) saves four small uploads."""
     torch = _torch()
     dev = grid.device
-    ob_lat = np.ascontiguousarray(ob_lat, dtype=np.float64)
-    ob_lon = np.ascontiguousarray(ob_lon, dtype=np.float64)
-    nobs = ob_lat.shape[0]
-    d_lat, d_lon = _dev_f64(ob_lat, dev), _dev_f64(ob_lon, dev)
-    d_sl = _dev_f64(np.sin(np.radians(ob_lat)), dev)
-    d_cl = _dev_f64(np.cos(np.radians(ob_lon)), dev)
+    if dev_tables is None:
+        ob_lat = np.ascontiguousarray(ob_lat, dtype=np.float64)
+        ob_lon = np.ascontiguousarray(ob_lon, dtype=np.float64)
+        d_lat, d_lon = _dev_f64(ob_lat, dev), _dev_f64(ob_lon, dev)
+        d_sl = _dev_f64(np.sin(np.radians(ob_lat)), dev)
+        d_cl = _dev_f64(np.cos(np.radians(ob_lon)), dev)
+    else:
+        d_lat, d_lon, d_sl, d_cl = dev_tables
+    nobs = d_lat.shape[0]
     idx4 = torch.empty((nobs, 4), dtype=torch.int64, device=dev)
     w4 = torch.empty((nobs, 4), dtype=torch.float64, device=dev)
     nex = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -136,7 +141,18 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False):
     return idx4, w4, nex
 
 
-def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, group=None):
+def pseudo_distance_order(grid: GridTables, lat, lon, npt):
+    """Flat indices of the npt grid points with the smallest pseudo-distance to (lat, lon), ordered by (distance,
+    flat index): nearest_points for any npt (state/ensemble.py:152-168)."""
+    torch = _torch()
+    d2 = torch.empty(grid.npts, dtype=torch.float64, device=grid.device)
+    _lib.call('exb_pseudo_distance', _lib.ptr(grid.sinlat), _lib.ptr(grid.coslon), grid.npts,
+              float(np.sin(np.radians(lat))), float(np.cos(np.radians(lon))), _lib.ptr(d2), _lib.stream_ptr())
+    order = torch.sort(d2, stable=True).indices[:npt]
+    return order.cpu().numpy()
+
+
+def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, group=None, obs_dev=None):
     """Y[nobs, nens] = H X for all obs (compute_ob_priors, assimilation/assimilation.py:36-49).
 
     X may also be a PINNED host tensor: the gather kernel then reads the <= 8 stencil rows per ob straight from
@@ -144,20 +160,25 @@ def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, gr
     being uploaded.
 
     With band=(y0, y1), X holds only that latitude band of the state: each rank sums the stencil points it
-    owns and the partial sums are all-reduced, so every rank ends with the same full Y."""
+    owns and the partial sums are all-reduced, so every rank ends with the same full Y.
+    obs_dev: the device copies of the per-ob tables made by upload_obs (saves re-uploading them)."""
     torch = _torch()
     dev = grid.device
-    idx4, w4, nex = stencil_search(grid, obs.lat, obs.lon)
-    row0 = torch.as_tensor(obs.row0).to(dev)
-    row1 = torch.as_tensor(obs.row1).to(dev)
-    tw0, tw1 = _dev_f64(obs.tw0, dev), _dev_f64(obs.tw1, dev)
-    # 8-point stencil = 4 space points x 2 time levels (index/weight bookkeeping only)
-    idx8 = torch.cat([row0[:, None] + idx4, row1[:, None] + idx4], dim=1)
-    w8 = torch.cat([tw0[:, None] * w4, tw1[:, None] * w4], dim=1)
-    if band is not None:
-        from .sharding import localize_stencil
-        idx8, w8 = localize_stencil(idx8, w8, nlev, grid.ny, grid.nx, band[0], band[1])
-    idx8, w8 = idx8.contiguous(), w8.contiguous()
+    if obs_dev is None or 'row0' not in obs_dev:
+        obs_dev = {'lat': _dev_f64(obs.lat, dev), 'lon': _dev_f64(obs.lon, dev),
+                   'sinlat': _dev_f64(np.sin(np.radians(obs.lat)), dev), 'coslon': _dev_f64(np.cos(np.radians(obs.lon)), dev),
+                   'row0': torch.as_tensor(np.ascontiguousarray(obs.row0, dtype=np.int64)).to(dev),
+                   'row1': torch.as_tensor(np.ascontiguousarray(obs.row1, dtype=np.int64)).to(dev),
+                   'tw0': _dev_f64(obs.tw0, dev), 'tw1': _dev_f64(obs.tw1, dev)}
+    idx4, w4, nex = stencil_search(grid, None, None, dev_tables=(obs_dev['lat'], obs_dev['lon'], obs_dev['sinlat'],
+                                                                   obs_dev['coslon']))
+    # 8-point stencil = 4 space points x 2 time levels, re-based to the band's shard (index/weight bookkeeping only)
+    y0, y1 = band if band is not None else (0, grid.ny)
+    idx8 = torch.empty((obs.nobs, 8), dtype=torch.int64, device=dev)
+    w8 = torch.empty((obs.nobs, 8), dtype=torch.float64, device=dev)
+    _lib.call('exb_stencil_combine', _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(obs_dev['row0']), _lib.ptr(obs_dev['row1']),
+              _lib.ptr(obs_dev['tw0']), _lib.ptr(obs_dev['tw1']), obs.nobs, grid.ny, grid.nx, y0, y1, _lib.ptr(idx8),
+              _lib.ptr(w8), _lib.stream_ptr())
     Y = torch.empty((obs.nobs, X.shape[1]), dtype=X.dtype, device=dev)
     _lib.call('exb_gather_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(idx8), _lib.ptr(w8), 8,
               obs.nobs, _lib.ptr(Y), _lib.stream_ptr())
@@ -215,10 +236,10 @@ class ObsPlan:
     the current stream compute the ob priors: the constructor only enqueues the counting pass (exb_obs_plan_create),
     finish() sizes the lists and enqueues the fill pass (exb_obs_plan_finish)."""
 
-    def __init__(self, obs_dev, geo, nobs, loc_mode, rank=0, world=1):
+    def __init__(self, obs_dev, geo, nobs, loc_mode, rank=0, world=1, block=1):
         torch = _torch()
         self.handle = C.c_void_p()
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.block = rank, world, block
         self.stream = torch.cuda.Stream(device=geo.device)
         ready = obs_dev.get('_ready')
         if ready is not None:
@@ -227,7 +248,7 @@ class ObsPlan:
             self.stream.wait_stream(torch.cuda.current_stream())
         if world > 1:           # lists of this rank's rows only (distributed solve)
             _lib.call('exb_obs_plan_create_dist', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode, rank,
-                      world, C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
+                      world, block, C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
         else:
             _lib.call('exb_obs_plan_create', _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs, loc_mode,
                       C.c_void_p(self.stream.cuda_stream), C.byref(self.handle))
@@ -265,11 +286,11 @@ def _dist_buffers(nobs, nens, dtype, device, group):
 
 
 def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan, group=None):
-    """Obs-space solve with the rows dealt round-robin to the ranks of `group` (one process per GPU of an NVLink
-    domain): every rank solves nobs/world rows and publishes their records into all ranks' record buffers over peer
-    memory (exb_obs_solve_dist_*); afterwards ye rows, means, records and the pair counter are summed over the group
-    so that every rank holds the complete result, as after the replicated solve.  Returns False (nothing done) when
-    the plan is dense / multi-block or symmetric memory is unavailable."""
+    """Obs-space solve with the rows dealt to the ranks of `group` (one process per GPU of an NVLink domain) in blocks
+    of plan.block consecutive obs: every rank solves nobs/world rows and publishes their records into all ranks'
+    record buffers over peer memory (exb_obs_solve_dist_*); afterwards ye rows, means, records and the pair counter
+    are summed over the group so that every rank holds the complete result, as after the replicated solve.  Returns
+    False (nothing done) when the plan is dense / multi-block or symmetric memory is unavailable."""
     torch = _torch()
     import torch.distributed as dist
     g = group if group is not None else dist.group.WORLD
@@ -298,7 +319,7 @@ def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, s
         return False
     if rc != 0:
         raise _lib.ExbError('exb_obs_solve_dist_%s failed (%d): %s' % (sfx, rc, lib.exb_last_error().decode('utf-8', 'replace')))
-    mine = (torch.arange(nobs, device=Yp.device) % world) == rank
+    mine = (torch.arange(nobs, device=Yp.device) // plan.block) % world == rank
     Yp.mul_(mine[:, None].to(Yp.dtype))
     Ym.mul_(mine.to(Ym.dtype))
     # NaN marks "not assimilated" in the records (post mean / variance): keep it out of the sum
@@ -319,6 +340,12 @@ def obs_dist_wanted(group):
     if os.environ.get('EXB_OBS_DIST', '1') != '1' or not dist.is_initialized():
         return False
     return dist.get_world_size(group) > 1 and dist.get_backend(group) == 'nccl'
+
+
+def obs_dist_block():
+    """Block size of the distributed obs-space solve's dealing (EXB_OBS_DIST_BLOCK, default 1 = round-robin)."""
+    import os
+    return max(1, int(os.environ.get('EXB_OBS_DIST_BLOCK', '1')))
 
 
 def obs_plan_wanted(loc_mode):
@@ -351,18 +378,49 @@ def fused_sweep_available(dtype, nens):
     return os.environ.get('EXB_SU_IMPL', 'pipe') == 'pipe'
 
 
+_OBS_FIELDS = ('value', 'error', 'lat', 'lon', 'halfwidth', 'sinlat', 'coslon', 'tw0', 'tw1', 'row0', 'row1')
+_STAGING = {}
+
+
 def upload_obs(obs: ObsArrays, device, loc_mode):
+    """Per-ob tables on the device + the obgeo block of exb_obs_prepare.  Everything goes up in ONE copy from a cached
+    page-locked staging buffer (eleven 8-byte fields + the assimilate flags per ob): small pageable copies cost a
+    host synchronisation each and may not queue behind bulk state copies."""
     torch = _torch()
-    d = {
-        'value': _dev_f64(obs.value, device),
-        'error': _dev_f64(obs.error, device),
-        'lat': _dev_f64(obs.lat, device),
-        'lon': _dev_f64(obs.lon, device),
-        'assimilate': torch.as_tensor(np.ascontiguousarray(obs.assimilate, dtype=np.uint8)).to(device),
-    }
-    d['halfwidth'] = _dev_f64(obs.halfwidth, device) if loc_mode == LOC_GC else None
-    geo = torch.empty((8, obs.nobs), dtype=torch.float64, device=device)
-    _lib.call('exb_obs_prepare', _lib.ptr(d['lat']), _lib.ptr(d['lon']), _lib.ptr(d['halfwidth']), obs.nobs,
+    n = obs.nobs
+    nf = len(_OBS_FIELDS)
+    key = (n, str(device))
+    ent = _STAGING.get(key)
+    if ent is None:
+        if len(_STAGING) > 8:
+            _STAGING.clear()
+        ent = {'host': torch.empty(nf * n * 8 + n, dtype=torch.uint8).pin_memory(), 'event': None}
+        _STAGING[key] = ent
+    if ent['event'] is not None:
+        ent['event'].synchronize()               # the previous upload from this buffer has left the host
+    hb = ent['host'].numpy()
+    f64 = hb[:nf * n * 8].view(np.float64).reshape(nf, n)
+    i64 = hb[:nf * n * 8].view(np.int64).reshape(nf, n)
+    f64[0], f64[1], f64[2], f64[3] = obs.value, obs.error, obs.lat, obs.lon
+    f64[4] = obs.halfwidth if loc_mode == LOC_GC else 1.0
+    np.sin(np.radians(f64[2]), out=f64[5])
+    np.cos(np.radians(f64[3]), out=f64[6])
+    f64[7], f64[8] = obs.tw0, obs.tw1
+    i64[9], i64[10] = obs.row0, obs.row1
+    hb[nf * n * 8:] = obs.assimilate
+    db = torch.empty(nf * n * 8 + n, dtype=torch.uint8, device=device)
+    db.copy_(ent['host'], non_blocking=True)
+    ent['event'] = torch.cuda.Event()
+    ent['event'].record()
+    df = db[:nf * n * 8].view(torch.float64).view(nf, n)
+    di = db[:nf * n * 8].view(torch.int64).view(nf, n)
+    d = {name: (di[i] if name in ('row0', 'row1') else df[i]) for i, name in enumerate(_OBS_FIELDS)}
+    d['assimilate'] = db[nf * n * 8:]
+    d['_buffer'] = db
+    if loc_mode != LOC_GC:
+        d['halfwidth'] = None
+    geo = torch.empty((8, n), dtype=torch.float64, device=device)
+    _lib.call('exb_obs_prepare', _lib.ptr(d['lat']), _lib.ptr(d['lon']), _lib.ptr(d['halfwidth']), n,
               loc_mode, _lib.ptr(geo), _lib.stream_ptr())
     d['_ready'] = torch.cuda.Event()
     d['_ready'].record()
@@ -396,74 +454,87 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
     assert X.is_contiguous()
     tm = _Timer(timing)
     tm.mark('start')
+    plan = None
     with torch.cuda.device(dev):
         if inflation is not None:
-            fac = np.ascontiguousarray(inflation, dtype=np.float64)
-            assert fac.shape == (nlev,)
-            _lib.call('exb_inflate_' + sfx, _lib.ptr(X), nrows, nens, fac.ctypes.data_as(C.c_void_p), nlev,
-                      ny * nx, _lib.stream_ptr())
+            fac = np.ascontiguousarray(inflation, dtype=np.float64).ravel()
+            # one factor per level (float / per-variable dict) or one per state row (per-dimension arrays)
+            assert fac.shape[0] in (nlev, nrows), (fac.shape, nlev, nrows)
+            _lib.call('exb_inflate_' + sfx, _lib.ptr(X), nrows, nens, fac.ctypes.data_as(C.c_void_p), fac.shape[0],
+                      nrows // fac.shape[0], _lib.stream_ptr())
+        if obs.nobs == 0:
+            # an assimilation window without observations: the reference's loop body never runs (ensrf.py:50) and
+            # the (inflated) prior comes back as the posterior
+            z = np.zeros(0)
+            return AnalysisResult(prior_mean=z, prior_var=z, post_mean=z, post_var=z, assimilated=np.zeros(0, dtype=bool),
+                                  ms=tm.result(), obs_solve='none')
         # (small host-to-device copies: callers that stream the state in on another stream do them first and pass
         # the result, or they would queue behind the state in the copy engine)
         obs_dev, geo = obs_device if obs_device is not None else upload_obs(obs, dev, loc_mode)
-        # predecessor lists of the obs-space solve: geometry only, started on a side stream now so that they are built
-        # while the host and this stream work on the ob priors
-        plan = None
-        dist_solve = band is not None and obs_plan_wanted(loc_mode) and obs_dist_wanted(group)
-        if dist_solve:
-            import torch.distributed as dist
-            plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode, dist.get_rank(group), dist.get_world_size(group))
-        elif obs_plan_wanted(loc_mode):
-            plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
-        if Y is None:
-            Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group)
-        elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
-            Yp, nex = Y
-        else:       # ob priors H.x computed by the caller (e.g. before the state was scattered)
-            Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
-        Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
-        _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
-        fused = fused_sweep_available(X.dtype, nens)
-        if not fused:
-            xm = torch.empty(nrows, dtype=X.dtype, device=dev)
-            _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
-        if plan is not None:
-            plan.finish()
-        tm.mark('setup')
-        rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
-        counters = torch.zeros(2, dtype=torch.int64, device=dev)
-        done = False
-        if dist_solve:
-            done = obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan, group=group)
-            if not done:            # dense graph or no peer memory: replicated solve with a full plan
-                plan.destroy()
+        try:
+            # predecessor lists of the obs-space solve: geometry only, started on a side stream now so that they are
+            # built while the host and this stream work on the ob priors
+            dist_solve = band is not None and obs_plan_wanted(loc_mode) and obs_dist_wanted(group)
+            if dist_solve:
+                import torch.distributed as dist
+                plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode, dist.get_rank(group), dist.get_world_size(group),
+                               obs_dist_block())
+            elif obs_plan_wanted(loc_mode):
                 plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
+            if Y is None:
+                Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group, obs_dev=obs_dev)
+            elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
+                Yp, nex = Y
+            else:       # ob priors H.x computed by the caller (e.g. before the state was scattered)
+                Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
+            Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
+            _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
+            fused = fused_sweep_available(X.dtype, nens)
+            if not fused:
+                xm = torch.empty(nrows, dtype=X.dtype, device=dev)
+                _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+            if plan is not None:
                 plan.finish()
-        if not done:
-            obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
-        tm.mark('obs_solve')
-        grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
-        if fused:
-            for ya, yb in (sweep_bands or [(0, ny)]):
-                if before_band is not None:
-                    before_band(ya, yb)
-                state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb)
-                if on_band_done is not None:
-                    on_band_done(ya, yb)
-            tm.mark('state_update')
-        else:
-            state_update(xm, X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
-            tm.mark('state_update')
-            _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
-        tm.mark('recombine')
-        rec_h = rec.cpu().numpy()
-        if plan is not None:
-            plan.destroy()
-        _lib.call('exb_obs_solve_async_status')
-        cnt = counters.cpu().numpy()
-        nex_h = int(nex.item())
+            tm.mark('setup')
+            rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
+            counters = torch.zeros(2, dtype=torch.int64, device=dev)
+            done = False
+            which = 'replicated' if band is not None else 'single'
+            if dist_solve:
+                done = obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan, group=group)
+                if done:
+                    which = 'distributed(block=%d)' % plan.block
+                else:                   # dense graph or no peer memory: replicated solve with a full plan
+                    plan.destroy()
+                    plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
+                    plan.finish()
+            if not done:
+                obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
+            tm.mark('obs_solve')
+            grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
+            if fused:
+                for ya, yb in (sweep_bands or [(0, ny)]):
+                    if before_band is not None:
+                        before_band(ya, yb)
+                    state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb)
+                    if on_band_done is not None:
+                        on_band_done(ya, yb)
+                tm.mark('state_update')
+            else:
+                state_update(xm, X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, sfx)
+                tm.mark('state_update')
+                _lib.call('exb_recombine_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
+            tm.mark('recombine')
+            rec_h = rec.cpu().numpy()
+            _lib.call('exb_obs_solve_async_status')
+            cnt = counters.cpu().numpy()
+            nex_h = int(nex.item())
+        finally:
+            if plan is not None:
+                plan.destroy()
     return AnalysisResult(prior_mean=rec_h[0], prior_var=rec_h[1], post_mean=rec_h[2], post_var=rec_h[3],
                           assimilated=rec_h[7] != 0.0, n_exact=nex_h, state_pairs=int(cnt[1]) * nlev,
-                          obs_pairs=int(cnt[0]), ms=tm.result())
+                          obs_pairs=int(cnt[0]), ms=tm.result(), obs_solve=which)
 
 
 def sweep_band_schedule(nlev, ny, nx, nbands=None):
@@ -498,7 +569,8 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
 
     With band=(y0, y1) X_host / out hold only that latitude band of a host-resident state sharded over the ranks of
     `group` (one process per GPU): every rank moves its own band over its own PCIe link, the partial ob priors are
-    all-reduced (NCCL), the obs-space solve is replicated and no other data crosses between ranks."""
+    all-reduced (NCCL), the obs-space solve is distributed over the ranks through NVLink peer memory (or replicated, see
+    res.obs_solve) and no other data crosses between ranks."""
     torch = _torch()
     _lib.require_device()
     Xh = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(X_host)
@@ -531,7 +603,7 @@ def analysis_host(X_host, nlev, lat2d, lon2d, obs: ObsArrays, loc_mode, inflatio
             if inflation is None and Xh.is_pinned():
                 # PCIe is used by one thing at a time: first the gather (25 % of the state in 800-byte pieces),
                 # then the band uploads, which overlap the obs-space solve and the sweep of earlier bands
-                Y = ob_priors(Xh, grid, obs, _sfx(xdtype), nlev=nlev, band=band, group=group)
+                Y = ob_priors(Xh, grid, obs, _sfx(xdtype), nlev=nlev, band=band, group=group, obs_dev=obs_device[0])
             arrived = {}
             copy_in.wait_stream(main)
             with torch.cuda.stream(copy_in):

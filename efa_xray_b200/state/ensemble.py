@@ -14,6 +14,8 @@ through libefa_xray_b200; the scalar haversine is plain Python.
 """
 from __future__ import print_function
 
+import json
+import weakref
 from collections import OrderedDict
 from copy import deepcopy
 
@@ -23,6 +25,49 @@ import efa_xray_b200 as _pkg
 from .. import _lib
 
 _COORD_NAMES = ['validtime', 'lat', 'lon', 'mem', 'x', 'y']
+_STATE_DIMS = ('validtime', 'y', 'x', 'mem')
+
+
+class _BlockPool(object):
+    """Page-locked host blocks for ensemble data.  The analysis reads the prior straight out of the state's block and
+    writes the posterior straight into a new one (no staging copies), which needs page-locked memory to be
+    asynchronous; cudaHostAlloc costs ~0.2 s per GB, so blocks of states that were garbage-collected are kept for
+    the next analysis of the same size (cycling).  Without a CUDA device the blocks are plain numpy arrays."""
+
+    def __init__(self, max_cached_bytes=16 << 30):
+        self.free = {}            # (nbytes) -> [torch uint8 tensors]
+        self.cached = 0
+        self.max_cached = max_cached_bytes
+
+    def alloc(self, shape, dtype):
+        """-> (ndarray of that shape, owner): `owner` is the torch tensor to hand back to release() (or None)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        try:
+            import torch
+            cuda = torch.cuda.is_available()
+        except ImportError:
+            cuda = False
+        if not cuda or nbytes == 0:
+            return np.empty(shape, dtype=dtype), None
+        lst = self.free.get(nbytes)
+        if lst:
+            owner = lst.pop()
+            self.cached -= nbytes
+        else:
+            owner = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return owner.numpy().view(dtype).reshape(shape), owner
+
+    def release(self, owner):
+        if owner is None:
+            return
+        nbytes = owner.numel()
+        if self.cached + nbytes <= self.max_cached:
+            self.free.setdefault(nbytes, []).append(owner)
+            self.cached += nbytes
+
+
+BLOCK_POOL = _BlockPool()
 
 
 class Variable(object):
@@ -183,6 +228,8 @@ class _LabelledDataset(object):
         new = self._like()
         new._data_vars = OrderedDict((k, Variable(v.dims, v.values.copy())) for k, v in self._data_vars.items())
         new._coords = OrderedDict((k, Variable(v.dims, v.values.copy())) for k, v in self._coords.items())
+        if hasattr(new, '_consolidate'):
+            new._consolidate()
         return new
 
     def copy(self, deep=True):
@@ -232,13 +279,79 @@ class _LabelledDataset(object):
 
 
 class EnsembleState(_LabelledDataset):
-    """Define an ensemble state vector (efa_xray/state/ensemble.py:15)."""
+    """Define an ensemble state vector (efa_xray/state/ensemble.py:15).
+
+    Storage: when every variable has dims (validtime, y, x, mem) and the same dtype, the data of all variables lives
+    in ONE contiguous block [nvar, ntimes, ny, nx, nmem] (page-locked when a CUDA device is present) and the
+    variables are views into it.  That block IS the reference's state-vector layout (ensemble.py:110-114), so
+    to_vect() is a reshape, the analysis uploads straight from it, and the posterior state adopts the buffer the
+    analysis was downloaded into."""
 
     @classmethod
     def from_vardict(cls, vardict, coorddict):
         """ensemble.py:25-36.  vardict: {name: (dims, array)}; coorddict: {name: array | (dims, array)}."""
         new = cls.__new__(cls)
         _LabelledDataset.__init__(new, vardict, coorddict)
+        new._consolidate()
+        return new
+
+    # ---- contiguous block -------------------------------------------------------------------------------
+    def _block_view(self):
+        """The [nvar, nt, ny, nx, nmem] block if every variable is still a view into it (in order), else None."""
+        blk = self.__dict__.get('_block')
+        if blk is None or len(self._data_vars) != blk.shape[0]:
+            return None
+        base = blk.__array_interface__['data'][0]
+        step = blk[0].nbytes
+        for i, v in enumerate(self._data_vars.values()):
+            a = v._values
+            if (v.dims != _STATE_DIMS or a.shape != blk.shape[1:] or a.dtype != blk.dtype or not a.flags.c_contiguous
+                    or a.__array_interface__['data'][0] != base + i * step):
+                return None
+        return blk
+
+    def _adopt_block(self, blk, owner=None):
+        """Make the variables views of blk [nvar, nt, ny, nx, nmem] (no copy); owner = pool token of the block."""
+        names = list(self._data_vars.keys())
+        assert blk.shape[0] == len(names)
+        for i, n in enumerate(names):
+            self._data_vars[n] = Variable(_STATE_DIMS, blk[i])
+        self.__dict__['_block'] = blk
+        if owner is not None:
+            # hand the page-locked block back to the pool when this state object goes away
+            self.__dict__['_block_finalizer'] = weakref.finalize(self, BLOCK_POOL.release, owner)
+
+    def _consolidate(self):
+        """Gather the variables into one contiguous block (adopting the caller's memory when it already is one)."""
+        if self._block_view() is not None:
+            return True
+        vs = list(self._data_vars.values())
+        if not vs or any(v.dims != _STATE_DIMS for v in vs) or len({v._values.shape for v in vs}) != 1 \
+                or len({v._values.dtype for v in vs}) != 1 or vs[0]._values.dtype not in (np.float64, np.float32):
+            self.__dict__['_block'] = None
+            return False
+        first = vs[0]._values
+        step = first.nbytes
+        base = first.__array_interface__['data'][0]
+        if step > 0 and all(v._values.flags.c_contiguous and v._values.__array_interface__['data'][0] == base + i * step
+                            for i, v in enumerate(vs)):
+            # the caller's arrays are consecutive slices of one buffer (e.g. block[v] views): adopt it as it is
+            blk = np.lib.stride_tricks.as_strided(first, shape=(len(vs),) + first.shape, strides=(step,) + first.strides)
+            self.__dict__['_block_keepalive'] = [v._values for v in vs]
+            self._adopt_block(blk)
+            return True
+        blk, owner = BLOCK_POOL.alloc((len(vs),) + first.shape, first.dtype)
+        for i, v in enumerate(vs):
+            blk[i] = v._values
+        self._adopt_block(blk, owner)
+        return True
+
+    def _new_with_block(self, blk, owner=None):
+        """A new state with this state's coordinates (copied) and variable names whose data is blk (adopted)."""
+        new = self._like()
+        new._coords = OrderedDict((k, Variable(v.dims, v.values.copy())) for k, v in self._coords.items())
+        new._data_vars = OrderedDict((k, None) for k in self._data_vars.keys())
+        new._adopt_block(blk, owner)
         return new
 
     @classmethod
@@ -277,20 +390,36 @@ class EnsembleState(_LabelledDataset):
 
     def shape(self):
         """Full shape (nvars, ntimes, ny, nx, nmems) of the stacked array."""
+        blk = self._block_view()
+        if blk is not None:
+            return blk.shape
         return self.to_array().shape
 
     # ---- vector form, ensemble.py:110-121
     def to_vect(self):
-        """Nstate x Nmems array, row order var -> validtime -> y -> x."""
+        """Nstate x Nmems array, row order var -> validtime -> y -> x.  When the state's data is one contiguous
+        block this is a READ-ONLY VIEW of it (no copy; take .copy() to get a private array, as the reference's
+        to_vect returns); otherwise the variables are stacked as in the reference."""
+        blk = self._block_view()
+        if blk is not None:
+            v = blk.reshape(self.nstate(), self.nmems())
+            v = v.view()
+            v.flags.writeable = False
+            return v
         return np.reshape(self.transpose('validtime', 'y', 'x', 'mem').to_array().values,
                           (self.nstate(), self.nmems()))
 
     def from_vect(self, instate):
         """Takes an Nstate x Nmems ndarray and updates the state accordingly."""
+        blk = self._block_view()
+        if blk is not None:
+            np.copyto(blk, np.reshape(instate, blk.shape))
+            return
         instate = np.reshape(instate, self.shape())
         statearr = self.to_array()
         statearr.values = instate
         self.update(statearr.to_dataset(dim='variable'))
+        self._consolidate()
 
     def ensemble_mean(self):
         return self.mean(dim='mem')
@@ -320,15 +449,18 @@ class EnsembleState(_LabelledDataset):
                                       'reference\'s 1-D branch (state/ensemble.py:185-192) is not ported')
 
     def nearest_points(self, lat, lon, npt=1):
-        """Indices (y, x) of the npt <= 4 grid points nearest to (lat, lon) under the reference's
+        """Indices (y, x) of the npt grid points nearest to (lat, lon) under the reference's
         pseudo-metric hypot(dsin(lat), dcos(lon)) (ensemble.py:152-168); ties go to the lowest flat index."""
-        from ..engine import stencil_search
+        from ..engine import stencil_search, pseudo_distance_order
         self._require_2d()
         if npt > 4:
-            raise NotImplementedError('nearest_points supports npt <= 4 (the forward operator uses 4)')
-        idx4, _, _ = stencil_search(self._grid_tables(), np.array([lat], dtype=np.float64),
-                                    np.array([lon], dtype=np.float64))
-        flat = idx4.cpu().numpy()[0, :npt]
+            # any npt (ensemble.py:165 takes the first npt of a full argsort): pseudo-distances of all points on
+            # the device, stable sort there (ties -> lowest flat index)
+            flat = pseudo_distance_order(self._grid_tables(), float(lat), float(lon), int(npt))
+        else:
+            idx4, _, _ = stencil_search(self._grid_tables(), np.array([lat], dtype=np.float64),
+                                        np.array([lon], dtype=np.float64))
+            flat = idx4.cpu().numpy()[0, :npt]
         return np.unravel_index(flat, self['lat'].shape)
 
     def interpolate(self, var, time, lat, lon):
@@ -378,14 +510,19 @@ class EnsembleState(_LabelledDataset):
         except ImportError:
             arrays = {'var__' + k: v.values for k, v in self._data_vars.items()}
             arrays.update({'coord__' + k: v.values for k, v in self._coords.items()})
-            arrays['__dims__'] = np.array(repr({k: v.dims for k, v in self.variables.items()}))
-            np.savez(filename, **arrays)
+            arrays['__dims__'] = np.array(json.dumps({k: list(v.dims) for k, v in self.variables.items()}))
+            with open(filename, 'wb') as f:          # exactly this file name (np.savez(name) would append .npz)
+                np.savez(f, **arrays)
 
     @classmethod
     def load_from_disk(cls, filename):
         """Inverse of the .npz branch of save_to_disk."""
         with np.load(filename, allow_pickle=False) as z:
-            dims = eval(str(z['__dims__']), {'__builtins__': {}})   # dict of tuples of str written above
+            dims = json.loads(str(z['__dims__']))
+            if not (isinstance(dims, dict) and all(isinstance(k, str) and isinstance(v, list) and
+                                                   all(isinstance(d, str) for d in v) for k, v in dims.items())):
+                raise ValueError('%s: malformed __dims__ record' % (filename,))
+            dims = {k: tuple(v) for k, v in dims.items()}
             vardict = {k[5:]: (dims[k[5:]], z[k]) for k in z.files if k.startswith('var__')}
             coorddict = {k[7:]: (dims[k[7:]], z[k]) for k in z.files if k.startswith('coord__')}
         return cls.from_vardict(vardict, coorddict)

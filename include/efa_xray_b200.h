@@ -50,6 +50,10 @@ int exb_version(void);                       /* 100*major + minor               
 const char *exb_last_error(void);            /* message of the last failure on this thread    */
 int exb_device_check(void);                  /* 0 if the current device can run the kernels   */
 int64_t exb_launch_count(void);              /* kernels launched by this library so far        */
+/* Work buffers are allocated stream-ordered from a memory pool owned by this library (one per device; other users of
+ * cudaMallocAsync are unaffected).  Freed blocks stay cached up to EXB_POOL_KEEP_GB (environment, default 32 GiB);
+ * exb_pool_trim returns cached blocks of the current device to the driver, keeping at most keep_bytes. */
+int exb_pool_trim(uint64_t keep_bytes);
 
 /* ---- geometry --------------------------------------------------------------------------- */
 /* Unit vectors of grid points from lat/lon in degrees; out is SoA double[3][npts].
@@ -88,6 +92,11 @@ int exb_stencil_search(const double *sinlat_g, const double *coslon_g, const dou
                        const double *ob_coslon, const double *ob_lat_deg, const double *ob_lon_deg,
                        int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream);
 
+/* Squared pseudo-distance (same roundings as exb_stencil_search) of one observation to all npts grid points: the
+ * sort key of nearest_points(npt) for any npt (state/ensemble.py:160-165). */
+int exb_pseudo_distance(const double *sinlat_g, const double *coslon_g, int64_t npts, double ob_sinlat,
+                        double ob_coslon, double *d2, void *stream);
+
 /* Same search for RECTILINEAR grids (lat a function of y only, lon of x only -- every regular lat-lon
  * grid): the squared pseudo-distance separates into A[y] + B[x], so the search costs O(ny + nx) per ob
  * instead of O(ny * nx).  Tables are per row / per column; results are bit-identical to
@@ -96,6 +105,15 @@ int exb_stencil_search_rect(const double *sinlat_y, const double *coslon_x, cons
                             const double *lon_x_deg, int64_t ny, int64_t nx, const double *ob_sinlat,
                             const double *ob_coslon, const double *ob_lat_deg, const double *ob_lon_deg,
                             int64_t nobs, int64_t *idx4, double *w4, int32_t *n_exact, void *stream);
+
+/* 8-point stencils of the full forward operator: the 4 space points at the two bracketing time levels with the
+ * products of space and time weights (state/ensemble.py:202-237).  row0/row1 = first state row of the ob's variable
+ * at its lower / upper time level, tw0/tw1 the time weights.  idx8 are row indices into a shard that holds grid rows
+ * [y_begin, y_end) of every level (0, ny: the full state); stencil points outside the band get weight 0, so that the
+ * ranks of a latitude-band decomposition produce partial sums that add up to H.x. */
+int exb_stencil_combine(const int64_t *idx4, const double *w4, const int64_t *row0, const int64_t *row1,
+                        const double *tw0, const double *tw1, int64_t nobs, int64_t ny, int64_t nx, int64_t y_begin,
+                        int64_t y_end, int64_t *idx8, double *w8, void *stream);
 
 /* Y[k][m] = sum_p w[k][p] * X[idx[k][p]][m], p < K (K <= 8): the gather + weighted sums of
  * interpolate (state/ensemble.py:226-237) for all obs at once (compute_ob_priors,
@@ -150,8 +168,10 @@ int exb_obs_solve_f32(float *Ym, float *Yp, const double *ob_value, const double
  * loc_mode) it was built from. */
 int exb_obs_plan_create(const double *obgeo, const uint8_t *ob_assimilate, int64_t nobs, int loc_mode, void *stream,
                         void **plan);
+/* lists of this rank's rows only: blocks of `block` consecutive obs are dealt round-robin to the ranks, rank r owns
+ * the obs j with (j / block) % world == r (block = 1: plain round-robin) */
 int exb_obs_plan_create_dist(const double *obgeo, const uint8_t *ob_assimilate, int64_t nobs, int loc_mode, int rank,
-                             int world, void *stream, void **plan);   /* lists of the rows rank + v*world only */
+                             int world, int block, void *stream, void **plan);
 int exb_obs_plan_finish(void *plan);
 int exb_obs_plan_destroy(void *plan);
 int exb_obs_solve_planned_f64(void *plan, double *Ym, double *Yp, const double *ob_value, const double *ob_error,
@@ -161,8 +181,8 @@ int exb_obs_solve_planned_f32(void *plan, float *Ym, float *Yp, const double *ob
                               const uint8_t *ob_assimilate, const double *obgeo, int64_t nobs, int nens,
                               int loc_mode, double *rec, unsigned long long *counters, void *stream);
 
-/* Obs-space solve distributed over the GPUs of one NVLink domain (<= 8): rank `rank` solves the obs rows j with
- * j % world == rank and publishes their records into the record buffers of EVERY rank over peer memory, so that the
+/* Obs-space solve distributed over the GPUs of one NVLink domain (<= 8): rank `rank` solves the obs rows its plan
+ * (exb_obs_plan_create_dist) lists and publishes their records into the record buffers of EVERY rank over peer memory, so that the
  * dependency waits of all ranks resolve locally; the serial chain (longest dependency path) is unchanged, the work per
  * GPU is 1/world.  P_peers[q] / S_peers[q] are pointers, valid on this device, to rank q's buffers (e.g. torch symmetric
  * memory): P nobs*32*MC elements of T (MC = 4 up to 128 members, 8 above), S nobs*2 doubles.  Preconditions: every
@@ -180,9 +200,11 @@ int exb_obs_solve_dist_f32(void *plan, float *Ym, float *Yp, const double *ob_va
 
 /* exb_obs_solve_* only enqueues its kernels (the dependency-driven variant synchronises the stream once, to size
  * its work lists, before the solve itself is launched).  Its kernels wait on each other inside the launch; a
- * watchdog ends a wait that can never be satisfied (corrupted inputs) instead of hanging the device.  After
+ * watchdog (wall clock, EXB_WATCHDOG_S seconds without progress, default 20 + 1e-4 nobs) ends a wait that can never be
+ * satisfied (corrupted inputs) instead of hanging the device.  Every solve has its own verdict word; after
  * synchronising the stream, this returns EXB_OK, or EXB_ERR_CUDA if the watchdog fired during the last
- * exb_obs_solve_* of this process (its outputs are then invalid). */
+ * exb_obs_solve_* issued by the CALLING THREAD (its outputs are then invalid; a state sweep launched from the same
+ * thread after such a solve exits without touching the state). */
 int exb_obs_solve_async_status(void);
 
 /* State sweep over one latitude-band shard: applies obs [ob_begin, ob_end) in serial order to every

@@ -238,32 +238,53 @@ def compute_ob_priors(state, obs):
 
 
 # ------------------------------------------------------------------------------------------
-# inflation (float and per-variable dict paths), assimilation/assimilation.py:52-118
+# inflation (float, per-variable dict and per-dimension paths), assimilation/assimilation.py:52-118
 # ------------------------------------------------------------------------------------------
 def inflate_state(state, inflation):
-    """Mutates `state` like the reference's float path (assimilation.py:62-69) and per-variable
-    dict path (:103-114)."""
+    """Restates inflate_state.  Float (assimilation.py:62-69) and per-variable entries (:101-114) mutate `state`
+    in place, as the reference does through `variables[v][:] = ...`.  Per-dimension entries ('validtime', 'x',
+    'y'; :83-100) multiply the perturbations of EVERY variable by the array broadcast along that dimension --
+    the reference rebinds `self.prior` to the new Dataset there, leaving the caller's object alone, so this
+    function RETURNS the state the rest of the update must use (a copy in that case)."""
     if isinstance(inflation, float):
-        items = [(v, inflation) for v in state.varnames]
-    else:
-        items = [(k, v) for k, v in inflation.items() if k in state.varnames]
-    for v, fac in items:
-        mean = state.fields[v].mean(axis=-1)
-        perts = state.fields[v] - mean[..., None]
-        state.fields[v][:] = perts * fac + mean[..., None]
+        for v in state.varnames:
+            mean = state.fields[v].mean(axis=-1)
+            perts = state.fields[v] - mean[..., None]
+            state.fields[v][:] = perts * inflation + mean[..., None]
+        return state
+    for k, v in inflation.items():                                   # dict order, as the reference iterates
+        if k in ['validtime', 'lat', 'lon', 'x', 'y']:
+            v = np.asarray(v, dtype=np.float64)
+            axis = {'validtime': 0, 'y': 1, 'x': 2}[k]                 # fields are [nt, ny, nx, nmem]
+            assert v.shape[0] == next(iter(state.fields.values())).shape[axis]   # assimilation.py:87-88
+            shape = [1, 1, 1, 1]
+            shape[axis] = v.shape[0]
+            new = state.copy()                                        # `self.prior = perts * infl + mean` (:96)
+            for name in new.varnames:
+                mean = state.fields[name].mean(axis=-1)
+                perts = state.fields[name] - mean[..., None]
+                new.fields[name] = perts * v.reshape(shape) + mean[..., None]
+            state = new
+        else:
+            if k not in state.varnames:                              # "Unable to find variable ... Skipping" (:105-107)
+                continue
+            mean = state.fields[k].mean(axis=-1)
+            perts = state.fields[k] - mean[..., None]
+            state.fields[k][:] = perts * v + mean[..., None]
+    return state
 
 
 def format_prior_state(state, obs, inflation=None):
     """assimilation/assimilation.py:120-154."""
     if inflation is not None:
-        inflate_state(state, inflation)
+        state = inflate_state(state, inflation)
     obmeans, obperts = compute_ob_priors(state, obs)
     prior = state.to_vect()
     xbm = prior.mean(axis=1)
     Xbp = prior - xbm[:, None]
     xbm = np.hstack((xbm, obmeans))
     Xbp = np.vstack((Xbp, obperts))
-    return xbm, Xbp
+    return xbm, Xbp, state
 
 
 # ------------------------------------------------------------------------------------------
@@ -323,7 +344,7 @@ def ensrf_update(state, obs, loc='GC', inflation=None):
     """EnSRF(state, obs, inflation=..., loc=...).update(), assimilation/ensrf.py:33-151 with
     format_posterior_state (assimilation/assimilation.py:157-171).  Returns (post_state, obs);
     `state` is modified only by inflation, as in the reference."""
-    xam, Xap = format_prior_state(state, obs, inflation)
+    xam, Xap, state = format_prior_state(state, obs, inflation)     # `state` is self.prior from here on
     xam, Xap = ensrf_loop(state, obs, xam, Xap, loc=loc)
     post_state = state.copy()
     Nstate = state.nstate()

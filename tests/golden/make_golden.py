@@ -53,7 +53,29 @@ CASES = {
     # more obs than one panel / batch, many overlapping supports, mixed radii and errors, skipped obs
     'gc_dense300': (dict(ny=37, nx=72, nmem=12, nvars=2, ntimes=1, nobs=300, cutoff_km=1500.0, seed=5,
                          frac_skip=0.05, mixed_error=True, mixed_radius=True), 'GC', None),
+    # inflation as a per-variable dict (assimilation.py:101-114), incl. a name that is not a state variable
+    'gc_inflate_vardict': (dict(ny=19, nx=36, nmem=8, nvars=3, ntimes=2, nobs=30, cutoff_km=5000.0, seed=6),
+                           'GC', {'var0': 1.3, 'var2': 1.7, 'nosuchvar': 2.0}),
+    # inflation per dimension (assimilation.py:83-100): arrays along validtime, y and x, plus one variable factor
+    'gc_inflate_dims': (dict(ny=19, nx=36, nmem=8, nvars=2, ntimes=2, nobs=30, cutoff_km=5000.0, seed=7),
+                        'GC', {'validtime': [1.1, 1.4], 'y': ('linspace', 1.0, 1.5, 19), 'var1': 1.2,
+                               'x': ('linspace', 1.3, 0.9, 36)}),
 }
+
+
+def decode_inflation(infl):
+    """JSON-able inflation spec -> what EnSRF takes: lists / ('linspace', a, b, n) become float arrays."""
+    if not isinstance(infl, dict):
+        return infl
+    out = {}
+    for k, v in infl.items():
+        if isinstance(v, (list, tuple)) and len(v) == 4 and v[0] == 'linspace':
+            out[k] = np.linspace(float(v[1]), float(v[2]), int(v[3]))
+        elif isinstance(v, (list, tuple)):
+            out[k] = np.array(v, dtype=np.float64)
+        else:
+            out[k] = v
+    return out
 
 
 def run_case(name, kw, loc, inflation):
@@ -68,13 +90,18 @@ def run_case(name, kw, loc, inflation):
     loc_state0 = obs[0].localize(state, type='GC') if loc == 'GC' else np.zeros((1, 1))
     loc_obs0 = obs[0].localize(obs, type='GC') if loc == 'GC' else np.zeros(1)
 
-    post_state, post_obs = EnSRF(state, obs, inflation=inflation, verbose=False, loc=loc).update()
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):     # "Unable to find variable ... Skipping"
+        post_state, post_obs = EnSRF(state, obs, inflation=decode_inflation(inflation), verbose=False, loc=loc).update()
     post_vect = post_state.to_vect()
     f = lambda attr: np.array([np.nan if getattr(o, attr) is None else float(getattr(o, attr))
                                for o in post_obs])
     out = dict(
         params=json.dumps(dict(kw=kw, loc=loc, inflation=inflation)),
         prior_checksum=np.array([prior_vect.sum(), np.abs(prior_vect).sum()]),
+        # the caller's state after the call (inflated in place by the float / per-variable forms only)
+        prior_after_checksum=np.array([state.to_vect().sum(), np.abs(state.to_vect()).sum()]),
         ye=ye, nearest=near, loc_state0=loc_state0, loc_obs0=loc_obs0,
         post=post_vect,
         prior_mean=f('prior_mean'), prior_var=f('prior_var'),
@@ -126,6 +153,9 @@ def function_vectors():
 
 
 if __name__ == '__main__':
-    function_vectors()
+    only = sys.argv[1:]
+    if not only:
+        function_vectors()
     for name, (kw, loc, infl) in CASES.items():
-        run_case(name, kw, loc, infl)
+        if not only or name in only:
+            run_case(name, kw, loc, infl)

@@ -62,3 +62,110 @@ def test_localize_stencil_keeps_only_band_rows():
     assert li[0, 1] == (0 * 3 + 2) * nx + 1 and li[0, 3] == 0 * nx + 0
     assert equal_bands(10, 3) == [(0, 3), (3, 7), (7, 10)]
     assert partition_bands(np.ones(10), 2) == [(0, 5), (5, 10)]
+
+
+def _small_state(**kw):
+    from efa_xray_b200.synth import make_case, build_objects
+    from efa_xray_b200.state.ensemble import EnsembleState
+    from efa_xray_b200.observation.observation import Observation
+    case = make_case(**dict(dict(ny=7, nx=9, nmem=5, nvars=2, ntimes=2, nobs=6, seed=11), **kw))
+    state, obs = build_objects(case, EnsembleState, Observation)
+    return case, state, obs
+
+
+def test_state_block_layout_is_the_state_vector():
+    """The variables of an EnsembleState are views of one [nvar, nt, ny, nx, nmem] block, which is the reference's
+    to_vect layout (state/ensemble.py:110-121): to_vect is a read-only view, from_vect writes through, a deep copy
+    is independent, and replacing a variable's array falls back to stacking."""
+    from copy import deepcopy
+    case, state, _ = _small_state()
+    want = case.to_vect()
+    v = state.to_vect()
+    assert v.shape == (state.nstate(), state.nmems()) == want.shape
+    np.testing.assert_array_equal(v, want)
+    assert not v.flags.writeable and np.shares_memory(v, state.variables['var0'].values)
+    assert state.shape() == (2, 2, 7, 9, 5)
+    state.variables['var1'][:] = state.variables['var1'].values * 2.0          # in place through a view
+    np.testing.assert_array_equal(state.to_vect()[state.nstate() // 2:], 2.0 * want[state.nstate() // 2:])
+    cp = deepcopy(state)
+    cp.from_vect(np.zeros_like(want))
+    assert np.abs(cp.to_vect()).max() == 0.0 and np.abs(state.to_vect()).max() > 0.0
+    assert np.shares_memory(cp.to_vect(), cp.variables['var0'].values)
+    # a variable whose array was replaced no longer aliases the block: to_vect stacks, as the reference does
+    state['var0'].values = np.ones_like(state['var0'].values)
+    w = state.to_vect()
+    assert w.flags.writeable and (w[:state.nstate() // 2] == 1.0).all()
+    np.testing.assert_array_equal(w[state.nstate() // 2:], 2.0 * want[state.nstate() // 2:])
+
+
+def test_state_adopts_a_callers_contiguous_buffer():
+    from efa_xray_b200.synth import make_case, build_objects
+    from efa_xray_b200.state.ensemble import EnsembleState
+    from efa_xray_b200.observation.observation import Observation
+    out = np.empty((3, 1, 5, 6, 4))
+    case = make_case(ny=5, nx=6, nmem=4, nvars=3, ntimes=1, nobs=2, seed=12, out=out)
+    state, _ = build_objects(case, EnsembleState, Observation)
+    assert np.shares_memory(state.to_vect(), out)          # no copy at construction
+    np.testing.assert_array_equal(state.to_vect(), out.reshape(-1, 4))
+
+
+def test_save_to_disk_round_trip_and_hostile_file(tmp_path):
+    """state/ensemble.py:269-273 (netCDF needs xarray; the archive carries the same variables, coordinates, dims)."""
+    from efa_xray_b200.state.ensemble import EnsembleState
+    _, state, _ = _small_state()
+    fn = str(tmp_path / 'ens_state.nc')
+    state.save_to_disk(fn)
+    back = EnsembleState.load_from_disk(fn)
+    np.testing.assert_array_equal(back.to_vect(), state.to_vect())
+    assert back.vars() == state.vars() and back.shape() == state.shape()
+    for k in ('lat', 'lon', 'validtime', 'mem', 'y', 'x'):
+        np.testing.assert_array_equal(back.coords[k].values, state.coords[k].values)
+        assert back.coords[k].dims == state.coords[k].dims
+    # the dims record is data, never code
+    bad = str(tmp_path / 'bad.npz')
+    np.savez(bad, __dims__=np.array("__import__('os').system('true')"), var__a=np.zeros(1))
+    with pytest.raises(ValueError):
+        EnsembleState.load_from_disk(bad)
+
+
+@pytest.mark.parametrize('inflation', [1.5, {'var1': 1.25, 'nosuch': 3.0},
+                                       {'validtime': np.array([1.1, 1.4]), 'y': np.linspace(1, 1.5, 7), 'var0': 1.2,
+                                        'x': np.linspace(1.3, 0.9, 9)}])
+def test_inflation_factor_tables_match_the_oracle(inflation, capsys):
+    """Assimilation._inflation_factors (one factor per level, or per state row for per-dimension arrays) applied as
+    (x - mean) * f + mean reproduces the oracle's restatement of assimilation.py:52-118."""
+    from efa_xray_b200.assimilation.assimilation import Assimilation
+    from oracle import ensrf_oracle as O
+    case, state, obs = _small_state()
+    fac = Assimilation(state, obs, inflation=inflation)._inflation_factors()
+    X = case.to_vect()
+    f = np.repeat(fac, X.shape[0] // fac.shape[0])
+    m = X.mean(axis=1, keepdims=True)
+    got = (X - m) * f[:, None] + m
+    want = O.inflate_state(O.State.from_case(case), inflation).to_vect()
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+    with pytest.raises(ValueError):                      # 2-D lat cannot carry a per-dimension array (nor in the reference)
+        Assimilation(state, obs, inflation={'lat': np.ones(7)})._inflation_factors()
+
+
+def test_obs_marshalling_is_vectorised_and_keeps_reference_errors():
+    from efa_xray_b200.assimilation.assimilation import Assimilation
+    from efa_xray_b200 import engine
+    case, state, obs = _small_state(offtime=True, frac_skip=0.3, mixed_radius=True)
+    a = Assimilation(state, obs)._obs_arrays(engine.LOC_GC)
+    np.testing.assert_array_equal(a.value, case.ob_value)
+    np.testing.assert_array_equal(a.lat, case.ob_lat)
+    np.testing.assert_array_equal(a.assimilate, case.ob_assimilate.astype(np.uint8))
+    np.testing.assert_array_equal(a.halfwidth[case.ob_assimilate], case.ob_halfwidth[case.ob_assimilate])
+    tlo, thi, wlo, whi, _ = engine.time_weights(case.times, case.ob_time)
+    np.testing.assert_array_equal(a.row0, (case.ob_var * 2 + tlo) * 63)
+    np.testing.assert_array_equal(a.tw1, whi)
+    assert Assimilation(state, [])._obs_arrays(engine.LOC_GC).nobs == 0          # an empty window is not an error
+    k = int(np.flatnonzero(case.ob_assimilate)[0])
+    obs[k].localize_radius = None
+    with pytest.raises(TypeError):                       # abs(None), observation.py:120
+        Assimilation(state, obs)._obs_arrays(engine.LOC_GC)
+    obs[k].localize_radius = 100.0
+    obs[k].obtype = 'nosuchvar'
+    with pytest.raises(KeyError):
+        Assimilation(state, obs)._obs_arrays(engine.LOC_GC)

@@ -27,6 +27,9 @@ def test_full_update_matches_reference(name):
         assert set(map(tuple, near[i].T)) == set(map(tuple, g['nearest'][i].T))
     post, obs = O.ensrf_update(st, obs, loc=p['loc'], inflation=p['inflation'])
     np.testing.assert_allclose(post.to_vect(), g['post'], rtol=1e-12)
+    # the caller's state afterwards: inflated in place by the float / per-variable forms, untouched by arrays
+    after = st.to_vect()
+    np.testing.assert_allclose([after.sum(), np.abs(after).sum()], g['prior_after_checksum'], rtol=1e-13)
     for attr in ('prior_mean', 'prior_var', 'post_mean', 'post_var'):
         np.testing.assert_allclose(_diag(obs, attr), g[attr], rtol=1e-11, equal_nan=True)
     assert np.array_equal([o.assimilated for o in obs], g['assimilated'])
