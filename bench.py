@@ -12,8 +12,12 @@ ensemble.  Three measurements share one JSON line:
   e2e       the same analysis through the host-buffer API (engine.analysis_host, which the Python
             EnSRF.update() uses): pinned host state -> H2D -> analysis -> D2H, copies inside the timing
   cpu_baseline  the CPU oracle's per-observation loop on a bounded sample, rank 0, N = 1 only
-For N > 1 (launched by torchrun, one rank per GPU) the state is sharded in latitude bands; the obs-space
-solve is replicated; NCCL carries the all-reduce of the ob priors.  In the e2e measurement the host-resident
+  e2e_api   (N = 1) wall time of the reference-shaped call itself, EnSRF(state, obs, loc='GC').update() on an
+            EnsembleState and a list of Observation objects (marshalling of 1e5 Python objects included)
+For N > 1 (launched by torchrun, one rank per GPU) the state is sharded in latitude bands; the obs-space solve
+is distributed over the ranks through NVLink peer memory (config.obs_solve says what actually ran); NCCL
+carries the all-reduce of the ob priors and of the solve's results; after the timed region the sharded
+analysis is gathered on rank 0 and compared with an unsharded analysis (sharded_check).  In the e2e measurement the host-resident
 state is sharded the same way: every rank uploads and downloads its own band over its own PCIe link
 (sharding.scatter_bands / gather_bands remain for callers whose state lives on one rank).  Total work is
 fixed as N grows: "scaling": "strong".
@@ -46,6 +50,8 @@ def parse():
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-api', action='store_true', help='skip the EnSRF(...).update() wall-time measurement (N = 1)')
+    ap.add_argument('--no-check', action='store_true', help='skip the sharded-vs-unsharded comparison (N > 1)')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='target CPU time of the baseline sample')
     ap.add_argument('--seed', type=int, default=0)
     return ap.parse_args()
@@ -394,6 +400,55 @@ def run_ours(args):
                'api': 'efa_xray_b200.engine.analysis_host (pinned host state in, pinned host analysis out%s)'
                       % ('' if world == 1 else '; state sharded over the ranks by latitude band, each rank moves its own band')}
 
+    # ---- N > 1: the sharded analysis against an unsharded one on rank 0 (outside every timed region) ----------
+    sharded_check = None
+    if world > 1 and not args.no_check:
+        X.copy_(X0)
+        engine.analysis_device(X, nlev, grid, obs, loc_mode, band=band)
+        full = torch.empty((nrows, nens), dtype=tdtype, device=dev) if rank == 0 else None
+        sharding.gather_bands(X, full, bands, nlev, ny, nx, nens, rank)
+        if rank == 0:
+            ref = Xh.to(dev).to(tdtype)
+            prior_max_inc = ref.clone()
+            engine.analysis_device(ref, nlev, grid, obs, loc_mode)
+            inc = float((ref - prior_max_inc).abs().max())
+            del prior_max_inc
+            diff = float((full - ref).abs().max())
+            tol = 1e-9 if args.dtype == 'f64' else 1e-3
+            sharded_check = {'max_abs_diff': diff, 'largest_increment': inc, 'rel_to_increment': diff / inc,
+                             'tolerance': tol, 'ok': bool(diff <= tol * inc),
+                             'what': 'sharded analysis gathered on rank 0 vs an unsharded analysis of the same inputs'}
+            del ref, full
+        dist.barrier()
+
+    # ---- N = 1: the reference-shaped call itself --------------------------------------------------------------
+    e2e_api = None
+    if world == 1 and not args.no_api and not args.no_e2e and args.dtype == 'f64':
+        from efa_xray_b200.state.ensemble import EnsembleState
+        from efa_xray_b200.observation.observation import Observation
+        from efa_xray_b200.assimilation.ensrf import EnSRF
+        state, oblist = synth.build_objects(case, EnsembleState, Observation)     # adopts the pinned buffer (no copy)
+        walls = []
+        for i in range(3):
+            for o in oblist:
+                o.prior_mean = o.post_mean = o.prior_var = o.post_var = None
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            post_state, _ = EnSRF(state, oblist, verbose=False, loc='GC').update()
+            torch.cuda.synchronize()
+            walls.append(1e3 * (time.perf_counter() - t0))
+            if i < 2:
+                del post_state                    # its page-locked block goes back to the pool for the next call
+        api_ms = min(walls[1:])
+        pv = np.array([o.post_var for o in oblist], dtype=np.float64)
+        e2e_api = {'value': nassim / (api_ms * 1e-3), 'unit': 'obs/s', 'ms_per_call': api_ms, 'wall_ms_all_calls': walls,
+                   'api': "efa_xray.assimilation.ensrf.EnSRF(state, obs, loc='GC', verbose=False).update() -- EnsembleState "
+                          "(page-locked block) + %d Observation objects in, new EnsembleState + diagnostics on the obs out; "
+                          "first call includes the page-locked allocation of the posterior block" % len(oblist),
+                   'post_var_matches_device_path': bool(np.allclose(pv, res.post_var, rtol=1e-9, equal_nan=True)),
+                   'posterior_checksum': float(np.abs(post_state.to_vect()[::997]).sum())}
+        del post_state, state
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -411,8 +466,8 @@ def run_ours(args):
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': workload_name(args, cfg), 'l2_policy': 'state (%.2f GB) >> L2; restored from a device copy each step'
-                   % (nrows * nens * esize / 1e9), 'parallelism': 'lat-bands x%d (work-balanced), obs-space solve replicated' % world,
-                   'bands': bands},
+                   % (nrows * nens * esize / 1e9), 'parallelism': 'lat-bands x%d (work-balanced), obs-space solve %s' % (world, res.obs_solve),
+                   'obs_solve': res.obs_solve, 'bands': bands},
         'state_updates_per_s': state_pairs / (ms_step * 1e-3),
         'state_row_updates': state_pairs, 'obs_assimilated': nassim,
         'phases_ms': phases, 'step_ms': step_ms,
@@ -431,7 +486,7 @@ def run_ours(args):
                                          'exb_measure_fp64_peak (DFMA loop), both in this run',
                           'note': 'achieved = algorithmic flop (4 Nens + 3 per (row, ob) pair with non-zero weight) / '
                                   'kernel time'},
-        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+        'e2e': e2e, 'e2e_api': e2e_api, 'sharded_check': sharded_check, 'gpu_launches': int(launches), 'clocks': clocks,
     }
 
     if world == 1 and not args.no_cpu_baseline and args.dtype == 'f64':

@@ -278,6 +278,7 @@ extern "C" int exb_obs_solve_async_status(void) {
     if (v == 0) return EXB_OK;
     exb_set_error("exb_obs_solve: a dependency wait never completed (watchdog, record %d); the obs-space records are invalid",
                   v - 1);
+    g_status_last = -1;                   // reported: later sweeps of this thread are not tied to that solve any more
     return EXB_ERR_CUDA;
 }
 

@@ -122,6 +122,37 @@ __device__ __forceinline__ double exb_asin_sqrt_over_sqrt(double a) {
     pe = fma(pe, a2, 1.0); po = fma(po, a2, 0.16666666666666666);   // c0, c1
     return fma(po, a, pe);
 }
+// Same series cut after 10 terms: the remainder is c10 a^10 < 5e-18 for a <= EXB_SHORT_AMAX = 0.03 (support angle
+// <= 20 degrees, 2200 km), i.e. below half an ulp of Q ~ 1.
+#define EXB_SHORT_AMAX 0.03
+__device__ __forceinline__ double exb_asin_sqrt_over_sqrt_short(double a) {
+    const double a2 = a * a;
+    double pe = 0.011551800896139705, po = 0.009761609529194078;   // c8, c9
+    pe = fma(pe, a2, 0.017352764423076924); po = fma(po, a2, 0.01396484375);   // c6, c7
+    pe = fma(pe, a2, 0.030381944444444444); po = fma(po, a2, 0.022372159090909092);   // c4, c5
+    pe = fma(pe, a2, 0.075); po = fma(po, a2, 0.044642857142857144);   // c2, c3
+    pe = fma(pe, a2, 1.0); po = fma(po, a2, 0.16666666666666666);   // c0, c1
+    return fma(po, a, pe);
+}
+template <bool SHORT>
+__device__ __forceinline__ double loc_weight_fast_t(double a, double inv_hw, double a_max) {
+    const bool inside = a < a_max;
+    a = fmin(fmax(a, 1e-30), SHORT ? EXB_SHORT_AMAX : EXB_FAST_AMAX);
+    double y = (double)rsqrtf((float)a);                       // 1/sqrt(a) to ~1e-7
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    const double s = a * y;                                    // sqrt(a)
+    const double q = SHORT ? exb_asin_sqrt_over_sqrt_short(a) : exb_asin_sqrt_over_sqrt(a);
+    const double r = (2.0 * EXB_R_EARTH) * inv_hw * s * q;
+    const double rc = fmin(fmax(r, 1.0), 2.0);
+    double ir = (double)__frcp_rn((float)rc);                  // 1/r on [1, 2]
+    ir = ir * fma(-rc, ir, 2.0);
+    ir = ir * fma(-rc, ir, 2.0);
+    const double p1 = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+    const double p2 = fma(fma(fma(fma(fma(r, 1.0 / 12.0, -0.5), r, 0.625), r, 5.0 / 3.0), r, -5.0), r, 4.0) - (2.0 / 3.0) * ir;
+    double w = (r <= 1.0) ? p1 : ((r < 2.0) ? p2 : 0.0);
+    return inside ? w : 0.0;
+}
 __device__ __forceinline__ double loc_weight_fast(double a, double inv_hw, double a_max) {
     const bool inside = a < a_max;
     a = fmin(fmax(a, 1e-30), EXB_FAST_AMAX);
@@ -139,6 +170,21 @@ __device__ __forceinline__ double loc_weight_fast(double a, double inv_hw, doubl
     double w = (r <= 1.0) ? p1 : ((r < 2.0) ? p2 : 0.0);
     return inside ? w : 0.0;
 }
+
+// candidate lists per coarse tile of the state sweeps (state_sweep_pipe.cu)
+#define SP_CT 4                       // coarse tile = SP_CT x SP_CT patches
+struct SweepLists {
+    float4 *caps = nullptr;
+    int *cnt = nullptr;
+    int64_t *off = nullptr;
+    int *list = nullptr;
+    const int64_t *tile_off = nullptr;    // off shifted so that it is indexed by absolute coarse-tile number
+    int nctx = 1, eq_row = -1;
+};
+bool sweep_lists_wanted(int loc_mode, int64_t ob_begin, int64_t ob_end);
+int sweep_build_lists(const double *grid_u, int64_t npts, int nx, int y_begin, int y_end, int bty, int btx, const float4 *scan,
+                      int64_t ob_begin, int64_t ob_end, cudaStream_t st, SweepLists *out);
+void sweep_free_lists(SweepLists &l, cudaStream_t st);
 
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };

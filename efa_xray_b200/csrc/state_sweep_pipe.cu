@@ -31,7 +31,6 @@
 #define SP_CW (16 - SP_PW)            // consumer warps
 #define SP_NT ((SP_CW + SP_PW) * 32)
 #define SP_ROWS (SP_CW * 8)           // state rows per CTA
-#define SP_CT 4                       // coarse tile = SP_CT x SP_CT patches
 #define SP_MAXSTAGES 16
 
 struct SpParams {
@@ -749,6 +748,56 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const int *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// host side: candidate lists per coarse tile (shared with state_sweep_2p.cu)
+// ------------------------------------------------------------------------------------------
+bool sweep_lists_wanted(int loc_mode, int64_t ob_begin, int64_t ob_end) {
+    const char *nolist = getenv("EXB_SWEEP_NOLIST");
+    return loc_mode == EXB_LOC_GC && !(nolist && atoi(nolist)) && ob_end - ob_begin > 4096;
+}
+
+// Builds, for every coarse tile (SP_CT x SP_CT patches of bty x btx grid points) that intersects grid rows
+// [y_begin, y_end), the ascending list of obs in [ob_begin, ob_end) whose support can touch the tile.  Synchronises the
+// stream once (list sizes).  out->tile_off is indexed by ABSOLUTE coarse-tile number (coarse row * nctx + coarse col).
+int sweep_build_lists(const double *grid_u, int64_t npts, int nx, int y_begin, int y_end, int bty, int btx, const float4 *scan,
+                      int64_t ob_begin, int64_t ob_end, cudaStream_t st, SweepLists *out) {
+    const int pr0 = y_begin / bty, pr1 = (y_end + bty - 1) / bty;
+    const int cty = bty * SP_CT, ctx = btx * SP_CT;
+    out->nctx = (nx + ctx - 1) / ctx;
+    const int cr0 = pr0 / SP_CT, cr1 = (pr1 + SP_CT - 1) / SP_CT;
+    const int ntiles = (cr1 - cr0) * out->nctx;
+    EXB_CUDA(exb_malloc_async(&out->caps, sizeof(float4) * ntiles, st));
+    EXB_CUDA(exb_malloc_async(&out->cnt, sizeof(int) * ntiles, st));
+    EXB_CUDA(exb_malloc_async(&out->off, sizeof(int64_t) * (ntiles + 1), st));
+    const unsigned gridw = (unsigned)ceil_div64((int64_t)ntiles * 32, 256);
+    sweep_tile_caps_kernel<<<gridw, 256, 0, st>>>(grid_u, npts, nx, y_begin, y_end, pr0, cty, ctx, out->nctx, ntiles, out->caps);
+    sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(out->caps, ntiles, scan, ob_begin, ob_end, out->cnt, nullptr, nullptr);
+    ExbHostWords hw;                   // this call's own mapped words: [0] list total, [1] equator row
+    const int rcw = exb_host_words_acquire(&hw);
+    if (rcw != EXB_OK) return rcw;
+    struct WordsGuard { ExbHostWords w; ~WordsGuard() { exb_host_words_release(w); } } wguard{hw};
+    sweep_scan_kernel<<<1, 1024, 0, st>>>(out->cnt, ntiles, out->off, hw.dev);
+    sweep_eq_row_kernel<<<1, 256, 0, st>>>(grid_u + 2 * npts, nx, y_begin, y_end, hw.dev + 1);
+    exb_count_launches(4);
+    EXB_CUDA(cudaStreamSynchronize(st));
+    const long long total = hw.host[0];
+    out->eq_row = (int)hw.host[1];
+    EXB_CUDA(exb_malloc_async(&out->list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
+    sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(out->caps, ntiles, scan, ob_begin, ob_end, nullptr, out->off, out->list);
+    exb_count_launches(1);
+    // the kernels index tiles by absolute coarse row: shift the offsets' base
+    out->tile_off = out->off - (int64_t)cr0 * out->nctx;
+    return exb_check_launch("sweep_tile_list_kernel");
+}
+
+void sweep_free_lists(SweepLists &l, cudaStream_t st) {
+    if (l.caps) cudaFreeAsync(l.caps, st);
+    if (l.cnt) cudaFreeAsync(l.cnt, st);
+    if (l.off) cudaFreeAsync(l.off, st);
+    if (l.list) cudaFreeAsync(l.list, st);
+    l.caps = nullptr; l.cnt = nullptr; l.off = nullptr; l.list = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 template <int NT3, typename TS, bool MG>
@@ -785,42 +834,18 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
     EXB_CUDA(cudaFuncSetAttribute(state_sweep_pipe_kernel<NT3, TS, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // candidate lists per coarse tile (localised runs only; the kernel walks the ob range otherwise)
-    float4 *caps = nullptr;
-    int *cnt = nullptr, *list = nullptr;
-    int64_t *off = nullptr;
+    SweepLists lists;
     p.tile_off = nullptr;
     p.tile_list = nullptr;
-    const char *nolist = getenv("EXB_SWEEP_NOLIST");
-    if (p.loc_mode == EXB_LOC_GC && !(nolist && atoi(nolist)) && p.ob_end - p.ob_begin > 4096) {
-        const int cty = bty * SP_CT, ctx = btx * SP_CT;
-        p.nctx = (p.nx + ctx - 1) / ctx;
-        const int cr0 = p.pr0 / SP_CT, cr1 = (pr1 + SP_CT - 1) / SP_CT;
-        const int ntiles = (cr1 - cr0) * p.nctx;
-        EXB_CUDA(exb_malloc_async(&caps, sizeof(float4) * ntiles, st));
-        EXB_CUDA(exb_malloc_async(&cnt, sizeof(int) * ntiles, st));
-        EXB_CUDA(exb_malloc_async(&off, sizeof(int64_t) * (ntiles + 1), st));
-        const unsigned gridw = (unsigned)ceil_div64((int64_t)ntiles * 32, 256);
-        sweep_tile_caps_kernel<<<gridw, 256, 0, st>>>(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, p.pr0, cty, ctx, p.nctx, ntiles, caps);
-        sweep_tile_list_kernel<false><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, cnt, nullptr, nullptr);
-        ExbHostWords hw;                   // this call's own mapped words: [0] list total, [1] equator row
-        const int rcw = exb_host_words_acquire(&hw);
-        if (rcw != EXB_OK) return rcw;
-        struct WordsGuard { ExbHostWords w; ~WordsGuard() { exb_host_words_release(w); } } wguard{hw};
-        sweep_scan_kernel<<<1, 1024, 0, st>>>(cnt, ntiles, off, hw.dev);
-        sweep_eq_row_kernel<<<1, 256, 0, st>>>(p.grid_u + 2 * p.npts, p.nx, p.y_begin, p.y_end, hw.dev + 1);
-        exb_count_launches(4);
-        EXB_CUDA(cudaStreamSynchronize(st));
-        const long long total = hw.host[0];
-        p.eq_row = (int)hw.host[1];
+    p.nctx = 1;
+    if (sweep_lists_wanted(p.loc_mode, p.ob_begin, p.ob_end)) {
+        const int rcl = sweep_build_lists(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, bty, btx, p.scan, p.ob_begin, p.ob_end, st, &lists);
+        if (rcl != EXB_OK) return rcl;
+        p.nctx = lists.nctx;
+        p.eq_row = lists.eq_row;
         p.pr_eq = p.eq_row / bty;
-        EXB_CUDA(exb_malloc_async(&list, sizeof(int) * (size_t)(total > 0 ? total : 1), st));
-        sweep_tile_list_kernel<true><<<gridw, 256, 0, st>>>(caps, ntiles, p.scan, p.ob_begin, p.ob_end, nullptr, off, list);
-        exb_count_launches(1);
-        // the kernel indexes tiles by absolute coarse row: shift the offsets' base
-        p.tile_off = off - (int64_t)cr0 * p.nctx;
-        p.tile_list = list;
-    } else {
-        p.nctx = 1;
+        p.tile_off = lists.tile_off;
+        p.tile_list = lists.list;
     }
     const int64_t nblocks = (int64_t)p.ntx * nty * p.nlc;
     int rc = EXB_OK;
@@ -832,13 +857,31 @@ static int sp_launch(SpParams &p, cudaStream_t st) {
         exb_count_launches(1);
         rc = exb_check_launch("state_sweep_pipe_kernel");
     }
-    if (caps) { cudaFreeAsync(caps, st); cudaFreeAsync(cnt, st); cudaFreeAsync(off, st); cudaFreeAsync(list, st); }
+    sweep_free_lists(lists, st);
     return rc;
+}
+
+template <typename TS>
+int exb_state_sweep_2p(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
+                       const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
+                       int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                       cudaStream_t st);
+void s2_patch_shape(int64_t nlev, int64_t ny, int64_t nx, int *Lc_out, int *bty_out, int *btx_out);
+
+// EXB_SP_IMPL = 2p (default: two-phase kernel, state_sweep_2p.cu) | v3 (the concurrent producer/consumer kernel above)
+static bool sp_use_2p() {
+    const char *e = getenv("EXB_SP_IMPL");
+    return !(e && strcmp(e, "v3") == 0);
 }
 
 // Row granularity of the patches for a state with nlev levels: sweeping row ranges whose edges are multiples of
 // this value never splits a patch between two calls.
 extern "C" int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx) {
+    if (sp_use_2p()) {
+        int Lc, bty, btx;
+        s2_patch_shape(nlev, ny, nx, &Lc, &bty, &btx);
+        return bty;
+    }
     const int Lc = nlev < SP_ROWS ? (int)nlev : SP_ROWS;
     const int G = SP_ROWS / Lc;
     int bty = 1, btx = G;
@@ -859,6 +902,11 @@ int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, i
                          const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
                          int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
                          cudaStream_t st) {
+    if (sp_use_2p()) {
+        const int rc = exb_state_sweep_2p<TS>(xm, Xp, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin, ob_end,
+                                              y_begin, y_end, loc_mode, counters, st);
+        if (rc != EXB_ERR_UNSUPPORTED) return rc;
+    }
     SpParams p;
     p.xm = xm; p.Xp = Xp; p.Yp = Yp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
     p.tile_off = nullptr; p.tile_list = nullptr;

@@ -47,6 +47,10 @@ def test_update_matches_reference_golden(name):
     assert post_obs is obs and post_state is not state
     if p['inflation'] is None:
         np.testing.assert_array_equal(state.to_vect(), prior)          # prior untouched
+    # the caller's state after the call, as the reference leaves it: inflated in place by a float / per-variable
+    # factors, untouched by per-dimension arrays (assimilation.py:65, :96, :113)
+    after = state.to_vect()
+    np.testing.assert_allclose([after.sum(), np.abs(after).sum()], g['prior_after_checksum'], rtol=1e-13)
     _check_post(post_state.to_vect(), g['post'], state.to_vect())
     for attr in ('prior_mean', 'prior_var', 'post_mean', 'post_var'):
         np.testing.assert_allclose(_diag(obs, attr), g[attr], rtol=1e-9, equal_nan=True)
@@ -371,11 +375,15 @@ def _analysis_with_env(case, env, bands=None):
     dict(ny=61, nx=120, nmem=50, nvars=2, ntimes=2, nobs=5000, cutoff_km=2500.0, seed=42),
     dict(ny=46, nx=90, nmem=24, nvars=11, ntimes=1, nobs=4500, cutoff_km=3000.0, seed=43),
     dict(ny=46, nx=90, nmem=7, nvars=1, ntimes=1, nobs=300, cutoff_km=3000.0, seed=44),
+    # ~2900 candidates per patch: more than one chunk of the two-phase kernel (rows parked between chunks), supports
+    # beyond the range of the branch-free weight function
+    dict(ny=31, nx=60, nmem=16, nvars=2, ntimes=1, nobs=7000, cutoff_km=9000.0, seed=45, frac_skip=0.02),
 ])
 def test_sweep_variants_agree(kw):
-    """The warp-specialised fused sweep (default), the same kernel without candidate lists, band-by-band calls,
-    and the three-call forms (split / sweep / recombine) on the earlier tensor-core kernel and on the vector
-    kernel all apply the same obs in the same order to every state row."""
+    """The two-phase fused sweep (default), the same kernel without candidate lists, band-by-band calls, the
+    concurrent producer/consumer kernel of round 1 (EXB_SP_IMPL=v3), and the three-call forms (split / sweep /
+    recombine) on the earlier tensor-core kernel and on the vector kernel all apply the same obs in the same order
+    to every state row."""
     case = make_case(**kw)
     prior = case.to_vect()
     ref, res0 = _analysis_with_env(case, {'EXB_SU_IMPL': 'mma', 'EXB_OBS_IMPL': 'persistent'})
@@ -383,6 +391,8 @@ def test_sweep_variants_agree(kw):
     ny = case.lat2d.shape[0]
     runs = {
         'pipe_fused': _analysis_with_env(case, {}),
+        'pipe_v3': _analysis_with_env(case, {'EXB_SP_IMPL': 'v3'}),
+        'pipe_v3_split': _analysis_with_env(case, {'EXB_SP_IMPL': 'v3', 'EXB_FUSED': '0'}),
         'pipe_nolist': _analysis_with_env(case, {'EXB_SWEEP_NOLIST': '1'}),
         'pipe_split': _analysis_with_env(case, {'EXB_FUSED': '0'}),
         'vector': _analysis_with_env(case, {'EXB_SU_IMPL': 'vector'}),
@@ -459,25 +469,82 @@ def _replay_rows(rows_prior, row_pts, grid_u_h, ye, rec, geo, loc_mode):
     return out
 
 
+def _engine_obs(case):
+    from efa_xray_b200 import engine
+    ny, nx = case.lat2d.shape
+    nt = len(case.times)
+    tlo, thi, wlo, whi, _ = engine.time_weights(case.times, case.ob_time)
+    return engine.ObsArrays(value=case.ob_value, error=case.ob_error, lat=case.ob_lat, lon=case.ob_lon,
+                            halfwidth=case.ob_halfwidth, assimilate=case.ob_assimilate.astype(np.uint8),
+                            row0=(case.ob_var * nt + tlo) * (ny * nx), row1=(case.ob_var * nt + thi) * (ny * nx),
+                            tw0=wlo, tw1=whi)
+
+
+def _gc_weights(a, invhw, amax):
+    """Gaspari-Cohn weights from haversine-a values (numpy restatement of observation.py:117-130)."""
+    R = 6371.0
+    ang = 2.0 * np.arcsin(np.sqrt(np.clip(a, 0.0, 1.0)))
+    r = R * ang * invhw
+    w = np.where(r <= 1.0, ((((-0.25 * r + 0.5) * r + 0.625) * r - 5.0 / 3.0) * r * r + 1.0),
+                 np.where(r < 2.0, (((((r / 12.0 - 0.5) * r + 0.625) * r + 5.0 / 3.0) * r - 5.0) * r + 4.0
+                                     - 2.0 / (3.0 * np.maximum(r, 1e-300))), 0.0))
+    return np.where(a < amax, w, 0.0)
+
+
+def _replay_obs_rows(js, Yp0, ye, rec, geo):
+    """Obs-space replay in numpy: row j of the ob-prior perturbations receives the updates of every assimilated
+    ob k < j in serial order (ensrf.py:95-141 restricted to the obs rows) and must arrive at ye_j, the row the
+    device published for ob j.  Independent of the CUDA solve kernels."""
+    out = np.empty((len(js), Yp0.shape[1]))
+    for i, j in enumerate(js):
+        x = Yp0[j].copy()
+        ks = np.flatnonzero(rec[7, :j] != 0.0)
+        d = geo[0:3, ks] - geo[0:3, j][:, None]
+        w = _gc_weights(0.25 * (d * d).sum(axis=0), geo[3, ks], geo[4, ks])
+        for k, wk in zip(ks[w != 0.0], w[w != 0.0]):
+            x -= (rec[6, k] * wk * (x @ ye[k]) * rec[5, k]) * ye[k]
+        out[i] = x
+    return out
+
+
+def _sample_rows(rng, ny, nx, nlev, n=20):
+    pts = np.concatenate([rng.integers(0, ny * nx, n), [0, nx - 1, (ny - 1) * nx, ny * nx - 1, (ny // 2) * nx,
+                                                        (ny // 2) * nx + nx - 1, 5 * nx + 7, (ny - 3) * nx + nx // 2]])
+    levs = rng.integers(0, nlev, pts.size)
+    return pts, levs * (ny * nx) + pts
+
+
+_CONFIG3 = {}
+
+
+def _config3():
+    """BASELINE config 3 (100 members, 721x1440x3, 1e5 obs, cutoff 2000 km), built once per test session."""
+    if not _CONFIG3:
+        from efa_xray_b200.synth import CONFIGS
+        cfg = dict(CONFIGS['config3'])
+        case = make_case(cutoff_km=2000.0, seed=0, **cfg)
+        _CONFIG3.update(cfg=cfg, case=case, obs_block=_obs_block(case))
+    return _CONFIG3
+
+
 def test_config3_full_size_properties():
     """BASELINE config 3 in full (100 members, 721x1440x3, 1e5 obs, cutoff 2000 km) through size-independent checks:
     (1) the dependency-driven and the panel obs-space solves agree on all 1e5 records; (2) a numpy replay of the
     serial update from those records reproduces the swept state on sampled rows (poles, equator, date line);
-    (3) obs-space replay of sampled obs rows; (4) variance can only shrink; (5) rows keep finite values."""
-    import os
+    (3) a numpy replay of sampled obs rows from the records arrives at the ye rows the device published;
+    (4) variance can only shrink; (5) rows keep finite values."""
     import torch
     from efa_xray_b200 import engine
-    from efa_xray_b200.synth import CONFIGS
-    cfg = dict(CONFIGS['config3'])
+    c3 = _config3()
+    cfg, case = c3['cfg'], c3['case']
     ny, nx, nens, nlev = cfg['ny'], cfg['nx'], cfg['nmem'], cfg['nvars'] * cfg['ntimes']
-    case = make_case(cutoff_km=2000.0, seed=0, **cfg)
     dev = torch.device('cuda', 0)
     prior = case.to_vect()
     X = torch.as_tensor(prior).to(dev)
-    obs, Ym, Yp = _obs_block(case)
+    obs, Ym, Yp = c3['obs_block']
     grid = engine.GridTables(case.lat2d, case.lon2d, dev)
     res = engine.analysis_device(X, nlev, grid, obs, engine.LOC_GC)
-    assert res.assimilated.all() and res.state_pairs > 7.0e9
+    assert res.assimilated.all() and res.state_pairs > 7.0e9 and res.obs_solve == 'single'
     # (1) obs-space solve variants on the full ob set
     a = _run_obs_solve(obs, Ym, Yp, 1, 'dag')
     b = _run_obs_solve(obs, Ym, Yp, 1, 'persistent')
@@ -492,18 +559,199 @@ def test_config3_full_size_properties():
     _, geo = engine.upload_obs(obs, dev, 1)
     geo_h, gu_h = geo.cpu().numpy(), grid.u.cpu().numpy()
     rng = np.random.default_rng(3)
-    pts = np.concatenate([rng.integers(0, ny * nx, 20), [0, nx - 1, (ny - 1) * nx, ny * nx - 1, (ny // 2) * nx,
-                                                         (ny // 2) * nx + nx - 1, 5 * nx + 7, (ny - 3) * nx + nx // 2]])
-    levs = rng.integers(0, nlev, pts.size)
-    rows = levs * (ny * nx) + pts
+    pts, rows = _sample_rows(rng, ny, nx, nlev)
     got = X[torch.as_tensor(rows, device=dev)].cpu().numpy()
     want = _replay_rows(prior[rows], pts, gu_h, ye, rec, geo_h, 1)
     inc = np.abs(want - prior[rows]).max()
     assert inc > 1e-3
     assert np.abs(got - want).max() <= 1e-9 * inc
+    # (3) replay sampled obs rows (late ones have the most predecessors) from the records
+    js = np.concatenate([rng.integers(0, obs.nobs, 12), [0, 1, obs.nobs - 1, obs.nobs - 2]])
+    want_ye = _replay_obs_rows(js, Yp.cpu().numpy(), ye, rec, geo_h)
+    assert np.abs(ye[js] - want_ye).max() <= 1e-9 * np.abs(Yp.cpu().numpy()[js]).max()
     # (5) the whole analysis is finite and its spread did not grow on the sampled rows
     assert bool(torch.isfinite(X).all())
     assert (got.std(axis=1) <= prior[rows].std(axis=1) * (1 + 1e-9)).all()
+
+
+@pytest.mark.parametrize('nobs,cutoff_km', [(20000, 2000.0), (5000, 5000.0)])
+def test_dag_solve_matches_oracle_on_config3_prefix(nobs, cutoff_km):
+    """The dependency-driven obs-space solve against the ORACLE (oracle.obs_space_solve, the reference's serial loop
+    on the obs rows, ensrf.py:61-149) on the first `nobs` observations of BASELINE config 3: truncating the ob
+    list is exact because ob k never depends on later obs.  Records, ye rows and diagnostics at 1e-9.  20 000 obs
+    at 2000 km: dependency chain ~1e3; 5 000 obs at 5000 km: every ob sees ~15 % of the earlier ones."""
+    from oracle import ensrf_oracle as O
+    c3 = _config3()
+    case = c3['case']
+    obs_all, Ym, Yp = c3['obs_block']
+    import dataclasses
+    obs = dataclasses.replace(obs_all, **{f.name: getattr(obs_all, f.name)[:nobs] for f in dataclasses.fields(obs_all)})
+    if cutoff_km != 2000.0:
+        obs = dataclasses.replace(obs, halfwidth=np.full(nobs, 0.5 * cutoff_km))
+    ym, yp = Ym[:nobs].contiguous(), Yp[:nobs].contiguous()
+    got_ym, got_ye, rec, npairs = _run_obs_solve(obs, ym, yp, 1, 'dag')
+    want = O.obs_space_solve(ym.cpu().numpy(), yp.cpu().numpy(), obs.value, obs.error, obs.halfwidth, obs.lat, obs.lon,
+                             obs.assimilate.astype(bool), loc='GC')
+    scale = np.abs(want['ye']).max()
+    assert np.abs(got_ye - want['ye']).max() <= 1e-9 * scale
+    np.testing.assert_allclose(rec[0], want['prior_mean'], rtol=1e-10)
+    np.testing.assert_allclose(rec[1], want['prior_var'], rtol=1e-9)
+    np.testing.assert_allclose(rec[2], want['post_mean'], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(rec[3], want['post_var'], rtol=1e-9, equal_nan=True)
+    # innovations are differences of O(280 K) numbers: absolute tolerance from the means
+    np.testing.assert_allclose(rec[4], want['innov'], rtol=1e-9, atol=1e-10 * 300.0)
+    nens = yp.shape[1]
+    np.testing.assert_allclose(rec[5], 1.0 / ((nens - 1) * want['kdenom']), rtol=1e-9)
+    np.testing.assert_allclose(rec[6], want['beta'], rtol=1e-9)
+    assert npairs > nobs
+
+
+def _sharded_analysis(case, nshards, Yfull=None):
+    """N LOGICAL latitude-band shards run one after the other on one device through engine.analysis_device(band=...),
+    exactly as N ranks would (work-balanced bands, offset shard, shard-local stencils, replicated obs-space solve;
+    without a process group the partial ob priors are summed here instead of all-reduced)."""
+    import torch
+    from efa_xray_b200 import engine, sharding
+    dev = torch.device('cuda', 0)
+    ny, nx = case.lat2d.shape
+    nlev = len(case.times) * len(case.varnames)
+    obs = _engine_obs(case)
+    grid = engine.GridTables(case.lat2d, case.lon2d, dev)
+    Xfull = torch.as_tensor(case.to_vect()).to(dev)
+    nens = Xfull.shape[1]
+    work = sharding.estimate_row_work(case.lat2d, case.lon2d, obs.lat, obs.lon, 2.0 * obs.halfwidth, obs.assimilate)
+    bands = sharding.partition_bands(work, nshards)
+    shards = [sharding.band_view(Xfull, nlev, ny, nx, a, b).contiguous().reshape(-1, nens) for a, b in bands]
+    # H.x as the ranks compute it: every shard sums the stencil points it owns, the partial sums add up
+    parts = [engine.ob_priors(Xs, grid, obs, 'f64', nlev=nlev, band=bd)[0] for Xs, bd in zip(shards, bands)]
+    Ysum = torch.stack(parts).sum(dim=0)
+    results = [engine.analysis_device(Xs, nlev, grid, obs, engine.LOC_GC, band=bd, Y=Ysum) for Xs, bd in zip(shards, bands)]
+    out = torch.empty_like(Xfull)
+    for Xs, (a, b) in zip(shards, bands):
+        sharding.band_view(out, nlev, ny, nx, a, b).copy_(Xs.view(nlev, b - a, nx, nens))
+    return out, Ysum, results, bands
+
+
+@pytest.mark.parametrize('kw', [
+    dict(ny=91, nx=180, nmem=100, nvars=3, ntimes=1, nobs=6000, cutoff_km=1500.0, seed=71, frac_skip=0.05, mixed_radius=True),
+    dict(ny=61, nx=120, nmem=50, nvars=2, ntimes=2, nobs=3000, cutoff_km=2500.0, seed=72, offtime=True),
+])
+def test_sharded_logical_ranks_match_unsharded(kw):
+    """The latitude-band path (engine.analysis_device(band=...); the reference's intended split is
+    assimilation.py:186-202) as 2, 4 and 8 logical shards on one device against the unsharded analysis.
+    The obs-space results are band-independent and must be IDENTICAL on every shard; the state agrees to rounding
+    (a shard's patches start at its own first row, so a row meets the same obs in the same order but grouped into
+    different batches of 8, which changes the last bits only)."""
+    import torch
+    from efa_xray_b200 import engine
+    case = make_case(**kw)
+    dev = torch.device('cuda', 0)
+    nlev = len(case.times) * len(case.varnames)
+    obs = _engine_obs(case)
+    grid = engine.GridTables(case.lat2d, case.lon2d, dev)
+    prior = case.to_vect()
+    Xref = torch.as_tensor(prior).to(dev)
+    Yref, _ = engine.ob_priors(Xref, grid, obs, 'f64')
+    ref = engine.analysis_device(Xref, nlev, grid, obs, engine.LOC_GC)
+    inc = float((Xref - torch.as_tensor(prior).to(dev)).abs().max())
+    for n in (2, 4, 8):
+        out, Ysum, results, bands = _sharded_analysis(case, n)
+        assert len(bands) == n and bands[0][0] == 0 and bands[-1][1] == case.lat2d.shape[0]
+        assert float((Ysum - Yref).abs().max()) <= 1e-12 * float(Yref.abs().max())
+        for r in results:
+            assert r.obs_solve == 'replicated'
+            for f in ('prior_mean', 'prior_var', 'post_mean', 'post_var', 'assimilated'):
+                np.testing.assert_array_equal(getattr(r, f), getattr(results[0], f))
+            np.testing.assert_allclose(r.prior_var, ref.prior_var, rtol=1e-10)
+            np.testing.assert_allclose(r.post_mean, ref.post_mean, rtol=1e-10, equal_nan=True)
+        assert sum(r.state_pairs for r in results) == pytest.approx(ref.state_pairs, rel=1e-4)
+        assert float((out - Xref).abs().max()) <= 1e-9 * inc
+        assert bool(torch.isfinite(out).all())
+
+
+def test_sharded_logical_ranks_config3():
+    """Same check at BASELINE config 3 (the configuration the multi-GPU numbers are quoted on), 8 logical shards."""
+    import torch
+    from efa_xray_b200 import engine
+    c3 = _config3()
+    case, cfg = c3['case'], c3['cfg']
+    dev = torch.device('cuda', 0)
+    nlev = cfg['nvars'] * cfg['ntimes']
+    obs = _engine_obs(case)
+    grid = engine.GridTables(case.lat2d, case.lon2d, dev)
+    out, Ysum, results, bands = _sharded_analysis(case, 8)
+    prior = torch.as_tensor(case.to_vect()).to(dev)
+    Xref = prior.clone()
+    ref = engine.analysis_device(Xref, nlev, grid, obs, engine.LOC_GC)
+    inc = float((Xref - prior).abs().max())
+    del prior
+    assert sum(r.state_pairs for r in results) == pytest.approx(ref.state_pairs, rel=1e-5)
+    np.testing.assert_allclose(results[3].post_var, ref.post_var, rtol=1e-9)
+    diff = float((out - Xref).abs().max())
+    assert diff <= 1e-9 * inc, (diff, inc)
+
+
+def _full_size_replay(cfg, cutoff_km, seed, dtypes=('f64',), n_rows=12):
+    """A BASELINE configuration in full through engine.analysis_device, checked by the numpy row replay from the
+    device's obs-space records on sampled rows.  Returns {dtype: (sampled analysis rows, result)} + the replay."""
+    import torch
+    from efa_xray_b200 import engine
+    ny, nx, nlev = cfg['ny'], cfg['nx'], cfg['nvars'] * cfg['ntimes']
+    case = make_case(cutoff_km=cutoff_km, seed=seed, **cfg)
+    dev = torch.device('cuda', 0)
+    obs = _engine_obs(case)
+    grid = engine.GridTables(case.lat2d, case.lon2d, dev)
+    prior = case.to_vect()
+    rng = np.random.default_rng(5)
+    pts, rows = _sample_rows(rng, ny, nx, nlev, n=n_rows)
+    out = {}
+    for dt in dtypes:
+        X = torch.as_tensor(prior).to(dev)
+        if dt == 'f32':
+            X = X.to(torch.float32)
+        res = engine.analysis_device(X, nlev, grid, obs, engine.LOC_GC)
+        assert bool(torch.isfinite(X).all())
+        out[dt] = (X[torch.as_tensor(rows, device=dev)].cpu().numpy().astype(np.float64), res)
+        del X
+    # records of the float64 obs-space solve for the replay
+    X = torch.as_tensor(prior).to(dev)
+    Yp, _ = engine.ob_priors(X, grid, obs, 'f64')
+    del X
+    Ym = torch.empty(obs.nobs, dtype=torch.float64, device=dev)
+    from efa_xray_b200 import _lib
+    _lib.call('exb_split_mean_pert_f64', _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, Yp.shape[1], _lib.stream_ptr())
+    _, ye, rec, _ = _run_obs_solve(obs, Ym, Yp, 1, 'dag')
+    _, geo = engine.upload_obs(obs, dev, 1)
+    want = _replay_rows(prior[rows], pts, grid.u.cpu().numpy(), ye, rec, geo.cpu().numpy(), 1)
+    return out, want, prior[rows]
+
+
+def test_config2_full_size_replay():
+    """BASELINE config 2 in full: 50 members, 361x720, 3 variables x 4 times (12 levels per patch), 5000 obs."""
+    from efa_xray_b200.synth import CONFIGS
+    out, want, prior_rows = _full_size_replay(dict(CONFIGS['config2']), 2000.0, seed=1)
+    got, res = out['f64']
+    inc = np.abs(want - prior_rows).max()
+    assert inc > 1e-3 and res.assimilated.all()
+    assert np.abs(got - want).max() <= 1e-9 * inc
+
+
+def test_config4_full_size_replay_f64_and_fp32_tolerance():
+    """BASELINE config 4 in full (100 members, 721x1440 x 10 levels, 1e5 obs): the float64 analysis against the
+    numpy replay at 1e-9 of the increment, and the float32 instantiation against it at the stated float32
+    tolerance: analysis within 1e-5 of the field magnitude, perturbations within 1e-3 of the ensemble spread."""
+    from efa_xray_b200.synth import CONFIGS
+    out, want, prior_rows = _full_size_replay(dict(CONFIGS['config4']), 2000.0, seed=2, dtypes=('f64', 'f32'), n_rows=6)
+    got, res = out['f64']
+    inc = np.abs(want - prior_rows).max()
+    assert inc > 1e-3 and res.assimilated.all()
+    assert np.abs(got - want).max() <= 1e-9 * inc
+    got32, res32 = out['f32']
+    assert np.abs(got32 - want).max() <= 1e-5 * np.abs(want).max()
+    pert = want - want.mean(axis=1, keepdims=True)
+    pert32 = got32 - got32.mean(axis=1, keepdims=True)
+    assert np.abs(pert32 - pert).max() <= 1e-3 * pert.std()
+    np.testing.assert_allclose(res32.post_var, res.post_var, rtol=2e-3)
 
 
 def test_edge_cases_skipped_single_and_polar_obs():

@@ -122,7 +122,7 @@ def test_blocked_gram_recurrence_equals_sequential_rank1_updates():
 
 def test_fast_localisation_weight_constants_and_accuracy():
     src = open(os.path.join(ROOT, 'efa_xray_b200', 'csrc', 'common.cuh')).read()
-    body = src[src.index('exb_asin_sqrt_over_sqrt'):src.index('loc_weight_fast')]
+    body = src[src.index('exb_asin_sqrt_over_sqrt'):src.index('EXB_SHORT_AMAX')]
     consts = {int(n): float(v) for v, n in re.findall(r'([0-9.]+(?:e-?[0-9]+)?)\s*[;,)][^\n]*?//\s*c(\d+)', body)}
     found = dict(re.findall(r'//\s*(c\d+), (c\d+)', body))
     coef = [float(x) for x in re.findall(r'fma\(p[eo], a2, ([0-9.e-]+)\)', body)] + \
@@ -137,6 +137,18 @@ def test_fast_localisation_weight_constants_and_accuracy():
         pe, po = pe * a2 + exact[2 * k], po * a2 + exact[2 * k + 1]
     q = po * a + pe
     np.testing.assert_allclose(np.sqrt(a) * q, np.arcsin(np.sqrt(a)), rtol=4e-16)
+    # the 10-term series of exb_asin_sqrt_over_sqrt_short: same coefficients c0..c9, valid up to EXB_SHORT_AMAX = 0.03
+    sbody = src[src.index('double exb_asin_sqrt_over_sqrt_short'):src.index('template <bool SHORT>')]
+    scoef = [float(x) for x in re.findall(r'fma\(p[eo], a2, ([0-9.e-]+)\)', sbody)] + \
+            [float(x) for x in re.findall(r'double pe = ([0-9.e-]+), po = ([0-9.e-]+);', sbody)[0]]
+    assert sorted(scoef) == sorted(exact[:10])
+    assert float(re.search(r'#define EXB_SHORT_AMAX ([0-9.]+)', src).group(1)) == 0.03
+    s_a = np.concatenate([np.logspace(-14, -3, 40), np.linspace(0.001, 0.03, 200)])
+    s_a2 = s_a * s_a
+    pe, po = exact[8], exact[9]
+    for k in range(3, -1, -1):
+        pe, po = pe * s_a2 + exact[2 * k], po * s_a2 + exact[2 * k + 1]
+    np.testing.assert_allclose(np.sqrt(s_a) * (po * s_a + pe), np.arcsin(np.sqrt(s_a)), rtol=4e-16)
     # Gaspari-Cohn through that path against the oracle's (reference) formulation, 2000 km support
     hw = 1000.0
     r = 2.0 * 6371.0 * np.sqrt(a) * q / hw
