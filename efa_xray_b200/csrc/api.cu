@@ -435,7 +435,7 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
                                    ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs, didx4.as<int64_t>(),
                                    dw4.as<double>(), dnex.as<int32_t>(), st));
     EXB_TRY(exb_stencil_combine(didx4.as<int64_t>(), dw4.as<double>(), drow.as<int64_t>(), drow.as<int64_t>() + nobs,
-                                dtw.as<double>(), dtw.as<double>() + nobs, nobs, ny, nx, 0, ny, didx8.as<int64_t>(),
+                                dtw.as<double>(), dtw.as<double>() + nobs, nobs, ny, nx, 0, ny, 0, didx8.as<int64_t>(),
                                 dw8.as<double>(), st));
 
     // ---- band schedule ----------------------------------------------------------------------------------

@@ -348,7 +348,7 @@ __global__ void gather_kernel(const T *__restrict__ X, int nens, const int64_t *
 __global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *__restrict__ w4,
                                 const int64_t *__restrict__ row0, const int64_t *__restrict__ row1,
                                 const double *__restrict__ tw0, const double *__restrict__ tw1, int64_t nobs,
-                                int64_t ny, int64_t nx, int64_t y_begin, int64_t y_end,
+                                int64_t ny, int64_t nx, int64_t y_begin, int64_t y_end, int diag,
                                 int64_t *__restrict__ idx8, double *__restrict__ w8) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nobs) return;
@@ -357,7 +357,9 @@ __global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *
         const int64_t lev = (h ? row1[k] : row0[k]) / npts;
         const double tw = h ? tw1[k] : tw0[k];
         for (int p = 0; p < 4; ++p) {
-            const int64_t pt = idx4[k * 4 + p], y = pt / nx, x = pt - y * nx;
+            // diag: idx4 holds indices n into a 1-D point list and the stencil point is (y, x) = (n, n), which is how the
+            // reference's 1-D lat/lon branch reads the state (state/ensemble.py:185-187, :226)
+            const int64_t pt = idx4[k * 4 + p], y = diag ? pt : pt / nx, x = diag ? pt : pt - y * nx;
             const bool inside = y >= y_begin && y < y_end;
             idx8[k * 8 + 4 * h + p] = inside ? (lev * nyl + (y - y_begin)) * nx + x : 0;
             w8[k * 8 + 4 * h + p] = inside ? tw * w4[k * 4 + p] : 0.0;
@@ -367,11 +369,11 @@ __global__ void stencil8_kernel(const int64_t *__restrict__ idx4, const double *
 
 extern "C" int exb_stencil_combine(const int64_t *idx4, const double *w4, const int64_t *row0, const int64_t *row1,
                                    const double *tw0, const double *tw1, int64_t nobs, int64_t ny, int64_t nx,
-                                   int64_t y_begin, int64_t y_end, int64_t *idx8, double *w8, void *stream) {
+                                   int64_t y_begin, int64_t y_end, int diag, int64_t *idx8, double *w8, void *stream) {
     EXB_REQUIRE(idx4 && w4 && row0 && row1 && tw0 && tw1 && idx8 && w8, "null pointer");
     EXB_REQUIRE(nobs > 0 && ny > 0 && nx > 0 && y_begin >= 0 && y_end <= ny && y_begin < y_end, "bad sizes");
     stencil8_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, (cudaStream_t)stream>>>(idx4, w4, row0, row1, tw0, tw1, nobs,
-                                                                                         ny, nx, y_begin, y_end, idx8, w8);
+                                                                                         ny, nx, y_begin, y_end, diag, idx8, w8);
     exb_count_launches(1);
     return exb_check_launch("stencil8_kernel");
 }

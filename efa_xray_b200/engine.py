@@ -88,11 +88,29 @@ class GridTables:
     nearest_points (state/ensemble.py:160-163, computed with numpy so that ties fall where they do on the
     host) and unit vectors for great-circle distances."""
 
-    def __init__(self, lat2d, lon2d, device):
+    def __init__(self, lat2d, lon2d, device, ny=None):
+        """lat2d / lon2d: 2-D (y, x) coordinates, or 1-D arrays of nx points with `ny` given: the reference's 1-D
+        lat/lon branch (state/ensemble.py:185-192, assimilation/ensrf.py:110-111), where localisation depends on x
+        only and the forward operator reads the state at (y, x) = (n, n) for a point index n."""
         torch = _torch()
         lat2d = np.ascontiguousarray(lat2d, dtype=np.float64)
         lon2d = np.ascontiguousarray(lon2d, dtype=np.float64)
-        assert lat2d.ndim == 2 and lat2d.shape == lon2d.shape, '2-D lat(y,x)/lon(y,x) required'
+        self.diag = lat2d.ndim == 1
+        if self.diag:
+            assert ny is not None and lat2d.shape == lon2d.shape
+            if ny < lat2d.shape[0]:
+                raise IndexError('1-D lat/lon state: the forward operator indexes y with the point index '
+                                 '(state/ensemble.py:226), which needs ny >= nx (ny=%d, nx=%d)' % (ny, lat2d.shape[0]))
+            self.lat1 = _dev_f64(lat2d, device)
+            self.lon1 = _dev_f64(lon2d, device)
+            self.sinlat1 = _dev_f64(np.sin(np.radians(lat2d)), device)
+            self.coslon1 = _dev_f64(np.cos(np.radians(lon2d)), device)
+            self.u1 = torch.empty((3, lat2d.shape[0]), dtype=torch.float64, device=device)
+            _lib.call('exb_grid_unitvec', _lib.ptr(self.lat1), _lib.ptr(self.lon1), lat2d.shape[0], _lib.ptr(self.u1),
+                      _lib.stream_ptr())
+            lat2d = np.ascontiguousarray(np.broadcast_to(lat2d[None, :], (ny, lat2d.shape[0])))
+            lon2d = np.ascontiguousarray(np.broadcast_to(lon2d[None, :], (ny, lon2d.shape[0])))
+        assert lat2d.ndim == 2 and lat2d.shape == lon2d.shape, '2-D lat(y,x)/lon(y,x) or 1-D lat(x)/lon(x) required'
         self.ny, self.nx = lat2d.shape
         self.npts = self.ny * self.nx
         self.device = device
@@ -101,7 +119,7 @@ class GridTables:
         self.sinlat = _dev_f64(np.sin(np.radians(lat2d)).ravel(), device)
         self.coslon = _dev_f64(np.cos(np.radians(lon2d)).ravel(), device)
         # rectilinear grid (lat = f(y), lon = f(x)): the nearest-point search separates (O(ny+nx) per ob)
-        self.rectilinear = bool((lat2d == lat2d[:, :1]).all() and (lon2d == lon2d[:1, :]).all())
+        self.rectilinear = bool((lat2d == lat2d[:, :1]).all() and (lon2d == lon2d[:1, :]).all()) and not self.diag
         if self.rectilinear:
             self.lat_y = _dev_f64(lat2d[:, 0], device)
             self.lon_x = _dev_f64(lon2d[0, :], device)
@@ -130,7 +148,11 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False, dev_ta
     idx4 = torch.empty((nobs, 4), dtype=torch.int64, device=dev)
     w4 = torch.empty((nobs, 4), dtype=torch.float64, device=dev)
     nex = torch.zeros(1, dtype=torch.int32, device=dev)
-    if grid.rectilinear and not force_general:
+    if grid.diag:                    # 1-D point list: the search runs over the nx points, idx4 are point indices
+        _lib.call('exb_stencil_search', _lib.ptr(grid.sinlat1), _lib.ptr(grid.coslon1), _lib.ptr(grid.lat1),
+                  _lib.ptr(grid.lon1), grid.nx, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat), _lib.ptr(d_lon),
+                  nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
+    elif grid.rectilinear and not force_general:
         _lib.call('exb_stencil_search_rect', _lib.ptr(grid.sinlat_y), _lib.ptr(grid.coslon_x), _lib.ptr(grid.lat_y),
                   _lib.ptr(grid.lon_x), grid.ny, grid.nx, _lib.ptr(d_sl), _lib.ptr(d_cl), _lib.ptr(d_lat),
                   _lib.ptr(d_lon), nobs, _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(nex), _lib.stream_ptr())
@@ -145,8 +167,10 @@ def pseudo_distance_order(grid: GridTables, lat, lon, npt):
     """Flat indices of the npt grid points with the smallest pseudo-distance to (lat, lon), ordered by (distance,
     flat index): nearest_points for any npt (state/ensemble.py:152-168)."""
     torch = _torch()
-    d2 = torch.empty(grid.npts, dtype=torch.float64, device=grid.device)
-    _lib.call('exb_pseudo_distance', _lib.ptr(grid.sinlat), _lib.ptr(grid.coslon), grid.npts,
+    n = grid.nx if grid.diag else grid.npts
+    d2 = torch.empty(n, dtype=torch.float64, device=grid.device)
+    _lib.call('exb_pseudo_distance', _lib.ptr(grid.sinlat1 if grid.diag else grid.sinlat),
+              _lib.ptr(grid.coslon1 if grid.diag else grid.coslon), n,
               float(np.sin(np.radians(lat))), float(np.cos(np.radians(lon))), _lib.ptr(d2), _lib.stream_ptr())
     order = torch.sort(d2, stable=True).indices[:npt]
     return order.cpu().numpy()
@@ -177,7 +201,7 @@ def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, gr
     idx8 = torch.empty((obs.nobs, 8), dtype=torch.int64, device=dev)
     w8 = torch.empty((obs.nobs, 8), dtype=torch.float64, device=dev)
     _lib.call('exb_stencil_combine', _lib.ptr(idx4), _lib.ptr(w4), _lib.ptr(obs_dev['row0']), _lib.ptr(obs_dev['row1']),
-              _lib.ptr(obs_dev['tw0']), _lib.ptr(obs_dev['tw1']), obs.nobs, grid.ny, grid.nx, y0, y1, _lib.ptr(idx8),
+              _lib.ptr(obs_dev['tw0']), _lib.ptr(obs_dev['tw1']), obs.nobs, grid.ny, grid.nx, y0, y1, int(grid.diag), _lib.ptr(idx8),
               _lib.ptr(w8), _lib.stream_ptr())
     Y = torch.empty((obs.nobs, X.shape[1]), dtype=X.dtype, device=dev)
     _lib.call('exb_gather_' + sfx, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(idx8), _lib.ptr(w8), 8,

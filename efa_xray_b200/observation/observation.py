@@ -50,7 +50,8 @@ class Observation:
         _lib.require_device()
         if isinstance(state, EnsembleState):
             grid = state._grid_tables()
-            u, n, shape, dev = grid.u, grid.npts, state['lat'].shape, grid.device
+            u, n = (grid.u1, grid.nx) if grid.diag else (grid.u, grid.npts)      # 1-D lat/lon: one weight per point
+            shape, dev = state['lat'].shape, grid.device
         else:
             dev = torch.device('cuda', torch.cuda.current_device())
             lat = torch.as_tensor(np.array([ob.lat for ob in state], dtype=np.float64)).to(dev)

@@ -439,20 +439,14 @@ class EnsembleState(_LabelledDataset):
         cached = getattr(self, '_grid_cache', None)
         if cached is None or cached[0] != key:
             _lib.require_device()
-            cached = (key, GridTables(lat, lon, torch.device('cuda', torch.cuda.current_device())))
+            cached = (key, GridTables(lat, lon, torch.device('cuda', torch.cuda.current_device()), ny=self.ny()))
             object.__setattr__(self, '_grid_cache', cached)
         return cached[1]
-
-    def _require_2d(self):
-        if len(self['lat'].shape) != 2:
-            raise NotImplementedError('efa_xray_b200 supports 2-D lat(y,x)/lon(y,x) coordinates only; the '
-                                      'reference\'s 1-D branch (state/ensemble.py:185-192) is not ported')
 
     def nearest_points(self, lat, lon, npt=1):
         """Indices (y, x) of the npt grid points nearest to (lat, lon) under the reference's
         pseudo-metric hypot(dsin(lat), dcos(lon)) (ensemble.py:152-168); ties go to the lowest flat index."""
         from ..engine import stencil_search, pseudo_distance_order
-        self._require_2d()
         if npt > 4:
             # any npt (ensemble.py:165 takes the first npt of a full argsort): pseudo-distances of all points on
             # the device, stable sort there (ties -> lowest flat index)
@@ -468,7 +462,6 @@ class EnsembleState(_LabelledDataset):
         space x linear weights in time (ensemble.py:170-239, weights as the reference computes them)."""
         from ..engine import ObsArrays, ob_priors, time_weights
         import torch
-        self._require_2d()
         tlo, thi, wlo, whi, outside = time_weights(self['validtime'].values, np.array([np.datetime64(time)]))
         if outside[0]:
             print("Interpolation is outside of time range in state!")
@@ -486,7 +479,9 @@ class EnsembleState(_LabelledDataset):
             raise IndexError('observation within 1 km of a grid point: the reference raises here '
                              '(state/ensemble.py:195-196); set efa_xray_b200.EXACT_MATCH_POLICY = "nearest" '
                              'to use the nearest point instead')
-        return Y[0].cpu().numpy().astype(np.float64)
+        out = Y[0].cpu().numpy().astype(np.float64)
+        # the reference's 1-D lat/lon branch returns the estimate with a leading axis of length 1 (ensemble.py:233-234)
+        return out[None, :] if grid.diag else out
 
     def haversine(self, loc1, loc2):
         """Great-circle distance in km between two (lat, lon) pairs (ensemble.py:241-252)."""
@@ -497,8 +492,9 @@ class EnsembleState(_LabelledDataset):
         """Haversine distance in km from every grid point to (lat, lon) (ensemble.py:254-267)."""
         import torch
         grid = self._grid_tables()
-        out = torch.empty(grid.npts, dtype=torch.float64, device=grid.device)
-        _lib.call('exb_localization_weights', _lib.ptr(grid.u), grid.npts, float(lat), float(lon), 1.0, 0,
+        u, n = (grid.u1, grid.nx) if grid.diag else (grid.u, grid.npts)
+        out = torch.empty(n, dtype=torch.float64, device=grid.device)
+        _lib.call('exb_localization_weights', _lib.ptr(u), n, float(lat), float(lon), 1.0, 0,
                   _lib.ptr(out), None, _lib.stream_ptr())
         return out.cpu().numpy().reshape(self['lat'].shape)
 

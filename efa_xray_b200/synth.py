@@ -189,6 +189,45 @@ def make_case(ny=181, nx=360, nmem=50, nvars=1, ntimes=1, nobs=500, cutoff_km=20
                           avoid_mirror_ties=avoid_mirror_ties))
 
 
+def make_case_1d(npts=24, nmem=8, nvars=1, ntimes=1, nobs=30, cutoff_km=4000.0, seed=0, frac_skip=0.0):
+    """A state with 1-D lat(x)/lon(x): the reference's second coordinate branch (state/ensemble.py:185-192,
+    assimilation/ensrf.py:110-111).  There the forward operator reads the state at (y, x) = (n, n) for a point index n
+    and the localisation weight of row (y, x) depends on x only, so the state is [nt, npts, npts, nmem] over a list of
+    npts scattered points.  Case.lat2d / lon2d hold the 1-D coordinate arrays."""
+    rng = np.random.default_rng(seed)
+    lat = np.degrees(np.arcsin(rng.uniform(-0.9, 0.9, npts)))
+    lon = rng.uniform(0.0, 360.0, npts)
+    times = (np.datetime64('2020-01-01T00:00:00', 's') + np.arange(ntimes) * np.timedelta64(6 * 3600, 's'))
+    varnames = ['var%d' % v for v in range(nvars)] if nvars > 1 else ['t2m']
+    phases = rng.uniform(0, 2 * np.pi, (len(_WAVES), 2))
+    basis = _wave_basis(lat, lon, phases)                                     # [npts, W]
+    out = np.empty((nvars, ntimes, npts, npts, nmem))
+    amp_truth = rng.normal(0.0, 1.0, (nvars, ntimes, len(_WAVES)))
+    for v in range(nvars):
+        for t in range(ntimes):
+            amp = rng.normal(0.0, 1.0, (len(_WAVES), nmem))
+            fld = basis @ amp + (_base(lat) + 10.0 * v + 0.5 * t)[:, None]     # [npts(x), nmem]
+            out[v, t] = fld[None, :, :] + 0.3 * rng.standard_normal((npts, npts, nmem))
+    fields = {name: out[v] for v, name in enumerate(varnames)}
+    # obs a few hundred km away from the points (never within 1 km of one)
+    k = rng.integers(0, npts, nobs)
+    ob_lat = np.clip(lat[k] + rng.uniform(1.0, 4.0, nobs) * rng.choice([-1.0, 1.0], nobs), -88.0, 88.0)
+    ob_lon = (lon[k] + rng.uniform(1.0, 4.0, nobs) * rng.choice([-1.0, 1.0], nobs)) % 360.0
+    ob_var = rng.integers(0, nvars, nobs)
+    tix = rng.integers(0, ntimes, nobs)
+    ob_basis = _wave_basis(ob_lat, ob_lon, phases)
+    truth = _base(ob_lat) + 10.0 * ob_var + 0.5 * tix + (ob_basis * amp_truth[ob_var, tix]).sum(axis=1)
+    ob_error = np.full(nobs, 1.0)
+    ob_value = truth + rng.standard_normal(nobs)
+    ob_assim = rng.uniform(0, 1, nobs) >= frac_skip if frac_skip > 0 else np.ones(nobs, dtype=bool)
+    return Case(lat2d=lat, lon2d=lon, times=times.astype('datetime64[s]'), varnames=varnames, fields=fields,
+                ob_value=ob_value, ob_lat=ob_lat, ob_lon=ob_lon, ob_time=times[tix].astype('datetime64[s]'),
+                ob_var=ob_var.astype(np.int64), ob_error=ob_error, ob_halfwidth=np.full(nobs, 0.5 * cutoff_km),
+                ob_assimilate=ob_assim,
+                meta=dict(npts=npts, nmem=nmem, nvars=nvars, ntimes=ntimes, nobs=nobs, cutoff_km=cutoff_km, seed=seed,
+                          frac_skip=frac_skip, one_d=True))
+
+
 # BASELINE.json configs (sizes from SURVEY.md section 8 header)
 CONFIGS = {
     'config1': dict(ny=181, nx=360, nmem=50, nvars=1, ntimes=1, nobs=500),
@@ -202,10 +241,11 @@ def build_objects(case, state_cls, ob_cls):
     """Turn a Case into (state, [obs]) for any package that follows the reference API
     (EnsembleState.from_vardict, ensemble.py:25-36; Observation(...), observation.py:18-36)."""
     import datetime as _dt
-    ny, nx = case.lat2d.shape
+    ny, nx = next(iter(case.fields.values())).shape[1:3]
     vardict = {name: (('validtime', 'y', 'x', 'mem'), case.fields[name]) for name in case.varnames}
+    cdims = ('y', 'x') if case.lat2d.ndim == 2 else ('x',)         # 1-D lat(x)/lon(x): make_case_1d
     coorddict = {'validtime': case.times.astype('datetime64[ns]'),
-                 'lat': (('y', 'x'), case.lat2d), 'lon': (('y', 'x'), case.lon2d),
+                 'lat': (cdims, case.lat2d), 'lon': (cdims, case.lon2d),
                  'mem': np.arange(case.nmem) + 1, 'y': np.arange(ny), 'x': np.arange(nx)}
     state = state_cls.from_vardict(vardict, coorddict)
     obs = []

@@ -110,10 +110,12 @@ int exb_stencil_search_rect(const double *sinlat_y, const double *coslon_x, cons
  * products of space and time weights (state/ensemble.py:202-237).  row0/row1 = first state row of the ob's variable
  * at its lower / upper time level, tw0/tw1 the time weights.  idx8 are row indices into a shard that holds grid rows
  * [y_begin, y_end) of every level (0, ny: the full state); stencil points outside the band get weight 0, so that the
- * ranks of a latitude-band decomposition produce partial sums that add up to H.x. */
+ * ranks of a latitude-band decomposition produce partial sums that add up to H.x.  diag != 0: idx4 holds indices n
+ * into a 1-D point list (states with 1-D lat/lon) and the stencil point is (y, x) = (n, n), as the reference's 1-D
+ * branch reads the state (state/ensemble.py:185-187, :226). */
 int exb_stencil_combine(const int64_t *idx4, const double *w4, const int64_t *row0, const int64_t *row1,
                         const double *tw0, const double *tw1, int64_t nobs, int64_t ny, int64_t nx, int64_t y_begin,
-                        int64_t y_end, int64_t *idx8, double *w8, void *stream);
+                        int64_t y_end, int diag, int64_t *idx8, double *w8, void *stream);
 
 /* Y[k][m] = sum_p w[k][p] * X[idx[k][p]][m], p < K (K <= 8): the gather + weighted sums of
  * interpolate (state/ensemble.py:226-237) for all obs at once (compute_ob_priors,

@@ -54,7 +54,8 @@ class Ob(object):
 
 class State(object):
     """Plain-array stand-in for EnsembleState (state/ensemble.py:15): fields[name] has dims
-    (validtime, y, x, mem); lat/lon are 2-D (y, x); times is datetime64."""
+    (validtime, y, x, mem); lat/lon are 2-D (y, x) -- or 1-D (x), the reference's second branch --; times is
+    datetime64."""
 
     def __init__(self, fields, varnames, lat2d, lon2d, times):
         self.fields = {k: np.array(fields[k], dtype=np.float64, copy=True) for k in varnames}
@@ -174,10 +175,17 @@ def nearest_points(state, lat, lon, npt=1):
 
 
 def space_weights(state, lat, lon):
-    """state/ensemble.py:179-200 (2-D lat/lon branch): 4 points, haversine, 1/d weights."""
-    closey, closex = nearest_points(state, lat, lon, npt=4)
-    distances = np.array([haversine((state.lat[y, x], state.lon[y, x]), (lat, lon))
-                          for y, x in zip(list(closey), list(closex))])
+    """state/ensemble.py:179-200: 4 points, haversine, 1/d weights.  With 1-D lat/lon (:185-192) the 4 point indices
+    are used for BOTH y and x, and everything carries a leading axis of length 1 (closen is a 1-tuple)."""
+    if len(state.lat.shape) == 2:
+        closey, closex = nearest_points(state, lat, lon, npt=4)
+        distances = np.array([haversine((state.lat[y, x], state.lon[y, x]), (lat, lon))
+                              for y, x in zip(list(closey), list(closex))])
+    else:
+        closen = nearest_points(state, lat, lon, npt=4)
+        closey = closen
+        closex = closen
+        distances = np.array([haversine((state.lat[n], state.lon[n]), (lat, lon)) for n in list(closen)])
     spaceweights = np.zeros(distances.shape)
     if (distances < 1.0).sum() > 0:
         spaceweights[:, distances.argmin()] = 1       # IndexError, as the reference (trap 3)
@@ -213,9 +221,15 @@ def interpolate(state, var, time, lat, lon):
     timeweights = time_weights(state, time)
     if timeweights is None:
         return None
-    interp = state.fields[var][:, closey, closex, :]                 # [nt, 4, Nens]
-    interp = (timeweights[:, None, None] * interp).sum(axis=0)      # [4, Nens]
-    interp = (spaceweights[:, None] * interp).sum(axis=0)           # [Nens]
+    interp = state.fields[var][:, closey, closex, :]                 # [nt, 4, Nens]   (1-D lat/lon: [nt, 1, 4, Nens])
+    if len(interp.shape) == 3:                                       # state/ensemble.py:229-237
+        interp = (timeweights[:, None, None] * interp).sum(axis=0)  # [4, Nens]
+    else:
+        interp = (timeweights[:, None, None, None] * interp).sum(axis=0)
+    if len(interp.shape) == 3:
+        interp = (spaceweights[:, :, None] * interp).sum(axis=1)    # [1, Nens]
+    else:
+        interp = (spaceweights[:, None] * interp).sum(axis=0)       # [Nens]
     return interp
 
 

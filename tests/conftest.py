@@ -9,7 +9,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 GOLDEN_CASES = ['gc_small', 'gc_multivar_offtime', 'noloc_small', 'gc_4deg', 'gc_inflate', 'gc_dense300',
-                'gc_inflate_vardict', 'gc_inflate_dims']
+                'gc_inflate_vardict', 'gc_inflate_dims', 'gc_1d_points']
 
 
 def pytest_configure(config):
@@ -39,6 +39,15 @@ def load_golden(name):
     p = json.loads(str(g['params']))
     p['inflation'] = decode_inflation(p['inflation'])
     return g, p
+
+
+def golden_case(p):
+    """The synthetic Case a golden file was generated from (its make_case / make_case_1d parameters)."""
+    from efa_xray_b200.synth import make_case, make_case_1d
+    kw = dict(p['kw'])
+    if kw.pop('one_d', False):
+        return make_case_1d(**kw)
+    return make_case(**kw)
 
 
 @pytest.fixture(scope='session')

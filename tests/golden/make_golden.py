@@ -35,7 +35,7 @@ from efa_xray.assimilation.ensrf import EnSRF                 # noqa: E402
 import efa_xray                                               # noqa: E402
 assert efa_xray.__file__.startswith('/root/reference'), efa_xray.__file__
 
-from efa_xray_b200.synth import make_case, build_objects      # noqa: E402
+from efa_xray_b200.synth import make_case, make_case_1d, build_objects      # noqa: E402
 
 # name -> (make_case kwargs, loc, inflation)
 CASES = {
@@ -60,6 +60,9 @@ CASES = {
     'gc_inflate_dims': (dict(ny=19, nx=36, nmem=8, nvars=2, ntimes=2, nobs=30, cutoff_km=5000.0, seed=7),
                         'GC', {'validtime': [1.1, 1.4], 'y': ('linspace', 1.0, 1.5, 19), 'var1': 1.2,
                                'x': ('linspace', 1.3, 0.9, 36)}),
+    # 1-D lat(x)/lon(x) coordinates: the reference's second branch (state/ensemble.py:185-192, ensrf.py:110-111)
+    'gc_1d_points': (dict(one_d=True, npts=24, nmem=8, nvars=2, ntimes=1, nobs=30, cutoff_km=4000.0, seed=8,
+                          frac_skip=0.1), 'GC', None),
 }
 
 
@@ -79,14 +82,17 @@ def decode_inflation(infl):
 
 
 def run_case(name, kw, loc, inflation):
-    kw = dict(kw, avoid_mirror_ties=True)
-    case = make_case(**kw)
+    if kw.get('one_d'):
+        case = make_case_1d(**{k: v for k, v in kw.items() if k != 'one_d'})
+    else:
+        kw = dict(kw, avoid_mirror_ties=True)
+        case = make_case(**kw)
     state, obs = build_objects(case, EnsembleState, Observation)
     prior_vect = state.to_vect().copy()
 
     # forward operator outputs for every ob, before anything is modified
     ye = np.array([ob.estimate(state) for ob in obs])
-    near = np.array([np.array(state.nearest_points(ob.lat, ob.lon, npt=4)) for ob in obs])   # [nobs,2,4]
+    near = np.array([np.array(state.nearest_points(ob.lat, ob.lon, npt=4)) for ob in obs])   # [nobs,2,4] (1-D: [nobs,1,4])
     loc_state0 = obs[0].localize(state, type='GC') if loc == 'GC' else np.zeros((1, 1))
     loc_obs0 = obs[0].localize(obs, type='GC') if loc == 'GC' else np.zeros(1)
 

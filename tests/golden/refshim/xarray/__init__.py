@@ -48,7 +48,8 @@ class Variable(object):
         k = 0
         for d in self.dims:
             if k < len(key):
-                if isinstance(key[k], slice):
+                # slices and integer ARRAYS keep the dimension (xarray: da[int array] is a DataArray over the same dim)
+                if isinstance(key[k], slice) or np.ndim(key[k]) == 1:
                     dims.append(d)
                 k += 1
             else:

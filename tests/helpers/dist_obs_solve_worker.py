@@ -19,6 +19,7 @@ def main():
     dev = torch.device('cuda', lr)
     dist.init_process_group('nccl', device_id=dev)
     nobs, nens, cutoff = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
+    block = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rng = np.random.default_rng(7)
     lat, lon = draw_obs_locations(rng, nobs, 181, 360)
     assim = (rng.uniform(0, 1, nobs) > 0.05).astype(np.uint8)
@@ -37,7 +38,7 @@ def main():
         ym, yp = Ym0.clone(), Yp0.clone()
         rec = torch.empty((8, nobs), dtype=torch.float64, device=dev)
         cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-        plan = engine.ObsPlan(obs_dev, geo, nobs, engine.LOC_GC, rank, world) if distributed else \
+        plan = engine.ObsPlan(obs_dev, geo, nobs, engine.LOC_GC, rank, world, block) if distributed else \
             engine.ObsPlan(obs_dev, geo, nobs, engine.LOC_GC)
         plan.finish()
         if distributed:
@@ -53,7 +54,7 @@ def main():
     ref = run(False)
     got = run(True)
     m = ~np.isnan(ref[3])
-    out = dict(ok=bool(got[0]), world=world, pairs=[got[4], ref[4]],
+    out = dict(ok=bool(got[0]), world=world, block=block, pairs=[got[4], ref[4]],
                maxdiff_yp=float(np.abs(got[2] - ref[2]).max()), maxdiff_ym=float(np.abs(got[1] - ref[1]).max()),
                nan_pattern_equal=bool((np.isnan(got[3]) == np.isnan(ref[3])).all()),
                maxdiff_rec=float(np.abs(got[3][m] - ref[3][m]).max()))

@@ -8,7 +8,7 @@ path only differs from numpy in summation order and 1-ulp libm differences).  fp
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, load_golden, golden_case
 from efa_xray_b200.synth import make_case, build_objects
 
 pytestmark = pytest.mark.gpu
@@ -39,7 +39,7 @@ def _check_post(post, ref_post, prior, tol_scale=1.0):
 def test_update_matches_reference_golden(name):
     EnsembleState, Observation, EnSRF = _api()
     g, p = load_golden(name)
-    case = make_case(**p['kw'])
+    case = golden_case(p)
     state, obs = build_objects(case, EnsembleState, Observation)
     prior = state.to_vect().copy()
     loc = p['loc'] if p['loc'] else False
@@ -61,7 +61,7 @@ def test_update_matches_reference_golden(name):
 def test_forward_operator_matches_reference_golden(name):
     EnsembleState, Observation, _ = _api()
     g, p = load_golden(name)
-    case = make_case(**p['kw'])
+    case = golden_case(p)
     state, obs = build_objects(case, EnsembleState, Observation)
     for k in (0, 1, len(obs) // 2, len(obs) - 1):
         ye = obs[k].estimate(state)
@@ -204,7 +204,7 @@ def test_host_buffer_c_abi_entry(pinned):
     import torch
     from efa_xray_b200 import _lib, engine
     g, p = load_golden('gc_multivar_offtime')
-    case = make_case(**p['kw'])
+    case = golden_case(p)
     X = np.ascontiguousarray(case.to_vect())
     if pinned:
         keep = torch.from_numpy(X).pin_memory()
@@ -782,3 +782,51 @@ def test_edge_cases_skipped_single_and_polar_obs():
     ref_post, ref_obs = _oracle_run(case, 'GC')
     _check_post(post.to_vect(), ref_post, state.to_vect())
     np.testing.assert_allclose(_diag(obs, 'post_var'), _diag(ref_obs, 'post_var'), rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize('obs_range,ob_error,inflation', [((1, 5), 1.0, 1.0), ((2, 4), 0.25, 2.0), ((1, 1), 2.0, 1.5)])
+def test_single_point_efa_demo_matches_notebook_arithmetic(obs_range, ob_error, inflation):
+    """efa_demo.ipynb cell 11 (`enkf`): one-point forecast trajectory, obs of its first valid times in shuffled order,
+    no localisation, optional inflation -- the library path against the notebook's numpy statements."""
+    from efa_xray_b200.demo import enkf, synthetic_point_ensemble
+    from oracle.demo_oracle import enkf_numpy
+    _, prior = synthetic_point_ensemble(ntimes=13, nmems=21, seed=4)
+    obs = [275.0, 275.0, 275.0, 275.0, 276.0]
+    n = obs_range[1] - obs_range[0] + 1
+    order = np.random.default_rng(8).permutation(n)
+    got = enkf(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order)
+    want = enkf_numpy(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert np.abs(want - prior).max() > 0.1
+    # the notebook shuffles the obs on every call; its variance (ddof 0) and covariance (ddof 1) normalisations differ
+    # (cell 11, lines 64 and 75), so the result depends on the order even without localisation: check a second order
+    order2 = order[::-1].copy()
+    np.testing.assert_allclose(enkf(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order2),
+                               enkf_numpy(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order2),
+                               rtol=1e-12)
+
+
+def test_one_dimensional_latlon_state_matches_reference_golden():
+    """States with 1-D lat(x)/lon(x) (state/ensemble.py:185-192, ensrf.py:110-111): nearest points, the forward
+    operator (leading axis of length 1, state read at (y, x) = (n, n)) and the x-only localisation against the
+    unmodified reference; the full update is covered by test_update_matches_reference_golden[gc_1d_points]."""
+    EnsembleState, Observation, _ = _api()
+    g, p = load_golden('gc_1d_points')
+    case = golden_case(p)
+    state, obs = build_objects(case, EnsembleState, Observation)
+    assert state['lat'].shape == (24,) and state.shape() == (2, 1, 24, 24, 8)
+    for k in (0, 7, len(obs) - 1):
+        near = state.nearest_points(obs[k].lat, obs[k].lon, npt=4)
+        assert len(near) == 1 and set(near[0].tolist()) == set(g['nearest'][k][0].tolist())
+        ye = obs[k].estimate(state)
+        assert ye.shape == (1, 8)
+        np.testing.assert_allclose(ye, g['ye'][k], rtol=1e-12)
+    w = obs[0].localize(state)
+    assert w.shape == (24,)
+    np.testing.assert_allclose(w, g['loc_state0'], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(obs[0].localize(obs), g['loc_obs0'], rtol=1e-10, atol=1e-13)
+    # any npt (ensemble.py:165 takes the first npt of a full argsort): the first four of nine are the four
+    near4 = state.nearest_points(obs[0].lat, obs[0].lon, npt=4)
+    near9 = state.nearest_points(obs[0].lat, obs[0].lon, npt=9)
+    assert len(near9) == 1 and near9[0].shape == (9,) and near9[0][:4].tolist() == near4[0].tolist()
+    assert len(set(near9[0].tolist())) == 9

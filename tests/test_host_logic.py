@@ -169,3 +169,22 @@ def test_obs_marshalling_is_vectorised_and_keeps_reference_errors():
     obs[k].obtype = 'nosuchvar'
     with pytest.raises(KeyError):
         Assimilation(state, obs)._obs_arrays(engine.LOC_GC)
+
+
+def test_block_dealing_of_obs_rows_is_a_partition_in_increasing_order():
+    """The distributed obs-space solve deals blocks of consecutive obs to the ranks (exb_obs_plan_create_dist): the
+    v-th row of rank r is ((v // b) * world + r) * b + v % b.  The engine's ownership mask ((j // b) % world == r) and
+    the library's row count formula must describe the same partition, each rank's rows in increasing order."""
+    for nobs, world, b in ((10, 2, 1), (3001, 2, 256), (2501, 4, 7), (100000, 8, 256), (5, 8, 3)):
+        owner = (np.arange(nobs) // b) % world
+        seen = np.zeros(nobs, dtype=int)
+        for r in range(world):
+            cyc = b * world
+            rem = nobs % cyc - r * b
+            nrows = (nobs // cyc) * b + min(max(rem, 0), b)
+            v = np.arange(nrows)
+            rows = ((v // b) * world + r) * b + v % b
+            assert np.array_equal(rows, np.flatnonzero(owner == r))
+            assert (np.diff(rows) > 0).all()
+            seen[rows] += 1
+        assert (seen == 1).all()

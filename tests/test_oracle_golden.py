@@ -4,7 +4,7 @@ with the oracle and with the same golden vectors."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, load_golden, golden_case
 from efa_xray_b200.synth import make_case
 from oracle import ensrf_oracle as O
 
@@ -16,7 +16,7 @@ def _diag(obs, attr):
 @pytest.mark.parametrize('name', GOLDEN_CASES)
 def test_full_update_matches_reference(name):
     g, p = load_golden(name)
-    case = make_case(**p['kw'])
+    case = golden_case(p)
     st, obs = O.State.from_case(case), O.obs_from_case(case)
     prior = st.to_vect()
     np.testing.assert_allclose([prior.sum(), np.abs(prior).sum()], g['prior_checksum'], rtol=1e-13)
@@ -37,7 +37,7 @@ def test_full_update_matches_reference(name):
 
 def test_localization_vectors():
     g, p = load_golden('gc_small')
-    case = make_case(**p['kw'])
+    case = golden_case(p)
     st, obs = O.State.from_case(case), O.obs_from_case(case)
     np.testing.assert_allclose(O.localize(obs[0], st), g['loc_state0'], rtol=1e-13, atol=1e-16)
     np.testing.assert_allclose(O.localize(obs[0], obs), g['loc_obs0'], rtol=1e-13, atol=1e-16)
