@@ -153,6 +153,38 @@ __device__ __forceinline__ double loc_weight_fast_t(double a, double inv_hw, dou
     double w = (r <= 1.0) ? p1 : ((r < 2.0) ? p2 : 0.0);
     return inside ? w : 0.0;
 }
+// Lean form for warp-convergent callers (every lane of the warp must call it): the same arithmetic with the
+// special-function seeds taken in double format (MUFU.RSQ64H / RCP64H: no conversions, no libm fix-up code), no
+// clamps (values outside the support may become Inf/NaN on the way and are discarded by the final SELECT), and only
+// the Gaspari-Cohn branch the warp needs when all of its lanes fall on the same side of r = 1.
+template <bool SHORT>
+__device__ __forceinline__ double loc_weight_lean(double a, double inv_hw, double a_max) {
+    const double ap = a + 1e-300;                              // a = 0 (ob on a grid point): r = 0, weight 1
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ap));    // ~2^-22
+    const double hm = -0.5 * ap;
+    y = y * fma(hm, y * y, 1.5);
+    y = y * fma(hm, y * y, 1.5);
+    const double q = SHORT ? exb_asin_sqrt_over_sqrt_short(a) : exb_asin_sqrt_over_sqrt(a);
+    const double r = ((2.0 * EXB_R_EARTH) * inv_hw) * ((ap * y) * q);
+    const bool inner = r <= 1.0;
+    double w;
+    if (__all_sync(0xffffffffu, inner)) {
+        w = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+    } else {
+        double ir;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ir) : "d"(r));
+        ir = ir * fma(-r, ir, 2.0);
+        ir = ir * fma(-r, ir, 2.0);
+        const double p2 = fma(fma(fma(fma(fma(r, 1.0 / 12.0, -0.5), r, 0.625), r, 5.0 / 3.0), r, -5.0), r, 4.0) - (2.0 / 3.0) * ir;
+        w = (r < 2.0) ? p2 : 0.0;
+        if (__any_sync(0xffffffffu, inner)) {
+            const double p1 = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+            w = inner ? p1 : w;
+        }
+    }
+    return (a < a_max) ? w : 0.0;
+}
 __device__ __forceinline__ double loc_weight_fast(double a, double inv_hw, double a_max) {
     const bool inside = a < a_max;
     a = fmin(fmax(a, 1e-30), EXB_FAST_AMAX);

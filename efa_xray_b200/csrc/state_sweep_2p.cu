@@ -8,13 +8,19 @@
 // sub-partition of their own, whose tensor pipe then sat idle (ceiling 75 % of the FP64 tensor peak, measured 58 %).
 // Here the two kinds of work never run at the same time:
 //   phase A  all 16 warps of the CTA: scan the patch's candidate obs (fp32 cap test over the coarse tile's list),
-//            evaluate omega[grid point][ob] = beta c1 GC(d) for batches of 8 obs and the batch's 8x8 Gram matrix, and
+//            evaluate omega[ob][grid point] = beta c1 GC(d) for batches of 8 obs and the batch's 8x8 Gram matrix, and
 //            write one block per batch to a per-CTA scratch area in global memory (L2-resident);
-//   phase B  15 consumer warps (8 state rows each, in registers for the whole patch) run  g = X Y^T -> 8-step
-//            recurrence -> X -= E Y  per batch; warp 15 only issues bulk copies (cp.async.bulk, completion on the
-//            stage's mbarrier by transaction bytes): the 8 ye rows of the batch straight from a padded copy of the ob
-//            ensembles (pseudo-member column and zero padding already in place) and the batch's omega/Gram block.
+//   phase B  the same 16 warps as consumers -- four per SM sub-partition, 8 state rows each, in registers for the whole
+//            patch -- run
+//            g = X Y^T -> 8-step recurrence -> X -= E Y  per batch; the stages are filled by bulk copies (cp.async.bulk,
+//            completion on the stage's mbarrier by transaction bytes) that the warps take turns issuing: the 8 ye rows
+//            of the batch straight from a padded copy of the ob ensembles (pseudo-member column and zero padding
+//            already in place) and the batch's omega/Gram block.
 // Every sub-partition's tensor pipe works in phase B and nothing but scalar FP64 runs in phase A.
+// Measured (scratch/ubench/consumer_ubench.cu, gpurun_out/r02b/c_consumer_ubench.txt): the consumer loop alone runs at
+// 27 clocks per (row, batch) as pure DMMA (97 % of the 16-clock issue interval), 29 with the shuffles, 32.5 with the
+// recurrence at 16 warps; 15 warps are no faster per warp than 16 (the sub-partition with four warps sets the pace),
+// a single accumulator chain in step 1 and folding the cross-block correction into the DMMA accumulator give 31.6.
 // The kernel is persistent (one CTA per SM, patches handed out by a ticket counter in heaviest-first order), a patch's
 // candidates are processed in chunks of at most S2_CAND so that the scratch area is bounded; between the chunks of one
 // patch the consumers park their rows in the scratch area (phase A needs the registers).
@@ -24,15 +30,17 @@
 // half warp, 4 consecutive doubles each) are both free of bank conflicts without an XOR swizzle of the columns, so the
 // rows can be copied in as they are.
 #include "common.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
-#define S2_NW 16                       // warps per CTA
-#define S2_CW 15                       // consumer warps (phase B); warp 15 issues the copies
+#define S2_NW 16                       // warps per CTA: four per SM sub-partition, 128 registers per thread
+#define S2_CW 16                       // every warp is a consumer in phase B (a 17th warp would put five warps on one
+                                       // sub-partition's 16 K registers: 96 per thread) and takes turns issuing the copies
 #define S2_NT (S2_NW * 32)
 #define S2_ROWS (S2_CW * 8)            // state rows per CTA
 #define S2_CAND 2048                   // candidate capacity of a chunk (256 batches)
-#define S2_SCAN 1024                   // list entries per scan step (2 per thread)
+#define S2_SCAN (2 * S2_NT)            // list entries per scan step (2 per thread)
 #define S2_MAXSTAGES 16
 
 struct S2Params {
@@ -50,6 +58,7 @@ struct S2Params {
     int *ticket;                      // patch dispenser
     double *scratch;                  // per CTA: S2_CAND/8 blocks of blk_doubles, then the parked rows
     const int *abort_flag;            // watchdog word of the obs-space solve that produced the records (may be null)
+    unsigned long long *prof;         // EXB_S2_PROF=1: clocks of warp 0 per phase, summed over CTAs (null: off)
     int64_t npts, nobs, ob_begin, ob_end, scratch_stride;
     int nlev, ny, nx, nens;
     int y_begin, y_end;               // grid rows [y_begin, y_end) of the shard are swept by this launch
@@ -107,7 +116,7 @@ template <int NT3> __host__ __device__ constexpr int s2_yst() { return ((8 * NT3
 // doubles of the ye-row region of a stage: 8 rows at q*YST + (q>>1)*4
 template <int NT3> __host__ __device__ constexpr int s2_ydoubles() { return 8 * s2_yst<NT3>() + 16; }
 
-// Stage layout (doubles): y rows [s2_ydoubles] | block = om[G][8] | Gram[64]
+// Stage layout (doubles): y rows [s2_ydoubles] | block = om[8][G] (ob-major) | Gram[64]
 template <int NT3, typename TS>
 __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params p) {
     TS *const gXp = static_cast<TS *>(p.Xp);
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_ring = reinterpret_cast<double *>(smem_raw);                                   // [nstages][stage_doubles]
     double *s_gu = s_ring + (size_t)p.nstages * p.stage_doubles;                             // [3][S2_ROWS]
-    double *s_sob = s_gu + 3 * S2_ROWS;                                                      // [S2_NW][6][8]
+    double *s_sob = s_gu + 3 * S2_ROWS;                                                      // [S2_NW][8][6]
     unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_sob + S2_NW * 48); // [S2_MAXSTAGES]
     unsigned long long *s_empty = s_full + S2_MAXSTAGES;                                      // [S2_MAXSTAGES]
     int *s_cand = reinterpret_cast<int *>(s_empty + S2_MAXSTAGES);                            // [S2_CAND]
@@ -149,16 +158,18 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
 
     double *const blocks = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
     double *const xsave = blocks + (size_t)(S2_CAND / 8) * BLK;
-    const bool is_consumer = warp < S2_CW;
     const bool fused = p.xm == nullptr;
-    // ring position of the next batch: the issuer and the consumers walk the same sequence
-    int rs = 0;
-    unsigned rpar = 0;
+    unsigned gbatch = 0;                         // batches that have gone through the ring so far (same in every thread)
     unsigned long long npairs = 0;
 
+    // phase clocks of thread 0 (only with p.prof): 0 patch setup, 1 scan, 2 blocks, 3 rows in/out, 4 phase B, 5 barriers
+    long long pt0 = 0, pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define S2_TICK(slot) do { if (p.prof && tid == 0) { const long long t_ = clock64(); pacc[slot] += t_ - pt0; pt0 = t_; } } while (0)
+    if (p.prof && tid == 0) pt0 = clock64();
     for (;;) {
         // ---- next patch -----------------------------------------------------------------------------------
         __syncthreads();                          // everybody is done with the previous patch's shared state
+        S2_TICK(5);
         if (tid == 0) s_misc[1] = atomicAdd(p.ticket, 1);
         __syncthreads();
         const int tk = s_misc[1];
@@ -229,11 +240,11 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
         }
 
         // this thread's state row (consumers: warp w holds rows 8w .. 8w+7, four lanes per row)
-        const int r = warp * 8 + n;               // row slot in the CTA (only meaningful for consumers)
+        const int r = warp * 8 + n;               // row slot in the CTA
         const int g = r / Lc, l = r % Lc;
         bool active = false;
         int64_t row = 0;
-        if (is_consumer && g < G && l0 + l < p.nlev) {
+        if (g < G && l0 + l < p.nlev) {
             const int gy = y0 + g / p.tx, gx = x0 + g % p.tx;
             if (gy >= p.y_begin && gy < p.y_end && gx < p.nx) {
                 active = true;
@@ -245,6 +256,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
         bool loaded = false, dirty = false;
 
         int64_t pos = lb;
+        S2_TICK(0);
         for (;;) {
             // =============================== PHASE A (1): candidates of this chunk ===============================
             int ncand = 0;
@@ -288,94 +300,156 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 pos += S2_SCAN;
                 __syncthreads();
             }
+            S2_TICK(1);
             if (ncand == 0) break;                // (the scan only stops empty-handed at the end of the list)
             const int nb = (ncand + 7) >> 3;
 
             // the consumers' rows are parked while the registers are needed for the weights
-            if (is_consumer && loaded) {
+            if (loaded) {
 #pragma unroll
                 for (int i = 0; i < 2 * NT3; ++i) xsave[(size_t)i * S2_NT + tid] = x[i];
             }
 
             // =============================== PHASE A (2): one block per batch ===============================
+            // Block of batch b (doubles): om[8][G] (ob-major: omega of ob q at grid point g) | Gram[64].
             {
                 double *sob = s_sob + warp * 48;
+                // the ring is idle in this phase: every warp stages the 8 ye rows of its current batch in it (cp.async)
+                // while it evaluates the weights, and forms the Gram matrix from there afterwards
+                double *stg = s_ring + (size_t)warp * (8 * YW);
+                const bool stage_rows = (size_t)S2_NW * 8 * YW <= (size_t)S * SD;
+                // scalars of the obs of a batch, held by lanes 0..7; loaded one batch ahead
+                struct ObSc { double ux, uy, uz, ihw, amax, cb; int kk; };
+                auto load_sc = [&](int b, ObSc &o) {
+                    o.ux = o.uy = o.uz = o.ihw = o.amax = o.cb = 0.0;
+                    o.kk = -1;
+                    if (b < nb && lane < 8 && 8 * b + lane < ncand) {
+                        const int kk = s_cand[8 * b + lane];
+                        o.kk = kk;
+                        o.ux = __ldg(p.geo + GEO_UX * p.nobs + kk); o.uy = __ldg(p.geo + GEO_UY * p.nobs + kk);
+                        o.uz = __ldg(p.geo + GEO_UZ * p.nobs + kk); o.ihw = __ldg(p.geo + GEO_INVHW * p.nobs + kk);
+                        o.amax = __ldg(p.geo + GEO_AMAX * p.nobs + kk);
+                        // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it
+                        o.cb = __ldg(p.rec + REC_C1 * p.nobs + kk) * __ldg(p.rec + REC_BETA * p.nobs + kk);
+                    }
+                };
+                ObSc cur, nxt;
+                load_sc(warp, cur);
                 for (int b = warp; b < nb; b += S2_NW) {
                     const int nq = min(8, ncand - 8 * b);
-                    const int kk = (lane < nq) ? s_cand[8 * b + lane] : -1;      // lanes 0..7: the obs of the batch
-                    double amax = 0.0;
-                    __syncwarp();
-                    if (lane < 8) {
-                        double ux = 0.0, uy = 0.0, uz = 0.0, ihw = 0.0, cb = 0.0;
-                        if (kk >= 0) {
-                            ux = __ldg(p.geo + GEO_UX * p.nobs + kk); uy = __ldg(p.geo + GEO_UY * p.nobs + kk);
-                            uz = __ldg(p.geo + GEO_UZ * p.nobs + kk); ihw = __ldg(p.geo + GEO_INVHW * p.nobs + kk);
-                            amax = __ldg(p.geo + GEO_AMAX * p.nobs + kk);
-                            // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it
-                            cb = __ldg(p.rec + REC_C1 * p.nobs + kk) * __ldg(p.rec + REC_BETA * p.nobs + kk);
-                        }
-                        sob[0 * 8 + lane] = ux; sob[1 * 8 + lane] = uy; sob[2 * 8 + lane] = uz;
-                        sob[3 * 8 + lane] = ihw; sob[4 * 8 + lane] = amax; sob[5 * 8 + lane] = cb;
+                    load_sc(b + S2_NW, nxt);
+                    __syncwarp();                                    // the previous batch's readers of sob / stg are done
+                    if (lane < 8) {          // per ob: ux uy uz 1/halfwidth a_max beta*c1
+                        *reinterpret_cast<double2 *>(sob + 6 * lane) = make_double2(cur.ux, cur.uy);
+                        *reinterpret_cast<double2 *>(sob + 6 * lane + 2) = make_double2(cur.uz, cur.ihw);
+                        *reinterpret_cast<double2 *>(sob + 6 * lane + 4) = make_double2(cur.amax, cur.cb);
                     }
-                    // operands of the Gram matrix (members only: the pseudo-member column is masked below); row n of
-                    // the batch, this lane's two members of every 8-member tile.  Issued before the weights so that the
-                    // L2 latency is covered by them.
-                    const int krow = __shfl_sync(0xffffffffu, kk, n);
-                    const double *yrow = p.Yw + (size_t)(krow >= 0 ? krow : p.nobs) * YW + 2 * c;
-                    double2 yv[NT3];
-#pragma unroll
-                    for (int t = 0; t < NT3; ++t) yv[t] = __ldg(reinterpret_cast<const double2 *>(yrow + 8 * t));
+                    if (stage_rows) {
+                        // 8 rows x YW doubles = 8 * YW / 2 chunks of 16 bytes, dealt to the lanes
+#pragma unroll 1
+                        for (int q = 0; q < 8; ++q) {
+                            const int kq = __shfl_sync(0xffffffffu, cur.kk, q);
+                            const double *src = p.Yw + (size_t)(kq >= 0 ? kq : p.nobs) * YW;
+                            for (int m = 2 * lane; m < YW; m += 64)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s2_smem(stg + q * YW + m)), "l"(src + m));
+                        }
+                        asm volatile("cp.async.commit_group;\n" ::);
+                    }
                     __syncwarp();
+                    S2_TICK(6);
                     // supports of all 8 obs within the range of the branch-free weight functions?
-                    const bool fast = __all_sync(0xffffffffu, lane >= 8 || amax <= EXB_FAST_AMAX);
-                    const bool shortser = __all_sync(0xffffffffu, lane >= 8 || amax <= EXB_SHORT_AMAX);
+                    const bool fast = __all_sync(0xffffffffu, lane >= 8 || cur.amax <= EXB_FAST_AMAX);
+                    const bool shortser = __all_sync(0xffffffffu, lane >= 8 || cur.amax <= EXB_SHORT_AMAX);
                     double *gblk = blocks + (size_t)b * BLK;
-                    // omega[g][q] = beta * loc / ((N-1) kdenom): lane-parallel over (grid point, ob) pairs, two
-                    // independent evaluations in flight per lane
-                    for (int i0 = lane; i0 < 8 * G; i0 += 64) {
-                        double omv[2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int i = i0 + 32 * j;
-                            const int q = i & 7, gg = min(i >> 3, G - 1);
-                            double w = 0.0;
-                            if (i < 8 * G && q < nq && s_gvalid[gg]) {
-                                w = 1.0;
-                                if (p.loc_mode == EXB_LOC_GC) {
-                                    const double a = hav_a(s_gu[gg], s_gu[S2_ROWS + gg], s_gu[2 * S2_ROWS + gg],
-                                                           sob[0 * 8 + q], sob[1 * 8 + q], sob[2 * 8 + q]);
-                                    w = shortser ? loc_weight_fast_t<true>(a, sob[3 * 8 + q], sob[4 * 8 + q])
-                                        : fast   ? loc_weight_fast_t<false>(a, sob[3 * 8 + q], sob[4 * 8 + q])
-                                                 : loc_weight(a, sob[3 * 8 + q], sob[4 * 8 + q]);
-                                }
-                                npairs += (w != 0.0 && lc == 0) ? 1 : 0;
-                            }
-                            omv[j] = w * sob[5 * 8 + q];
+                    // omega[q][g] = beta * loc / ((N-1) kdenom).  Grid points in whole groups of 32 are taken one per
+                    // lane with the obs of the batch in the outer loop: the point's unit vector stays in registers, the
+                    // ob's scalars are a broadcast read, and all lanes of a weight evaluation see the same ob (same side of
+                    // r = 1 unless the patch straddles the ob's half-width circle).  The remaining G % 32 points are
+                    // flattened with their obs over the lanes.  One evaluation at a time per lane: four warps per
+                    // sub-partition already saturate the scalar FP64 pipe (8 clocks latency, 2 per instruction).
+                    int npb = 0;
+                    auto weigh = [&](double gx, double gy, double gz, int q, bool valid) -> double {
+                        const double2 o01 = *reinterpret_cast<const double2 *>(sob + 6 * q);
+                        const double2 o23 = *reinterpret_cast<const double2 *>(sob + 6 * q + 2);
+                        const double2 o45 = *reinterpret_cast<const double2 *>(sob + 6 * q + 4);
+                        double w = 1.0;
+                        if (p.loc_mode == EXB_LOC_GC) {
+                            const double a = hav_a(gx, gy, gz, o01.x, o01.y, o23.x);
+                            w = shortser ? loc_weight_lean<true>(a, o23.y, o45.x)
+                                : fast   ? loc_weight_lean<false>(a, o23.y, o45.x)
+                                         : loc_weight(a, o23.y, o45.x);
                         }
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            if (i0 + 32 * j < 8 * G) gblk[i0 + 32 * j] = omv[j];
+                        w = valid ? w : 0.0;
+                        npb += (w != 0.0) ? 1 : 0;
+                        return w * o45.y;
+                    };
+                    const int nfull = G >> 5, R = G & 31;
+                    for (int sl = 0; sl < nfull; ++sl) {
+                        const int gg = lane + 32 * sl;
+                        const double gx = s_gu[gg], gy = s_gu[S2_ROWS + gg], gz = s_gu[2 * S2_ROWS + gg];
+                        const bool gval = s_gvalid[gg] != 0;
+#pragma unroll 2
+                        for (int q = 0; q < 8; ++q) gblk[q * G + gg] = weigh(gx, gy, gz, q, gval && q < nq);
                     }
-                    // Gram matrix of the batch
+                    if (R) {
+                        // pairs i = q * R + r of the last R points: q = i / R by a multiplication (exact for i < 2^20 / R)
+                        const int g0 = 32 * nfull, npr = 8 * R, nit = (npr + 31) >> 5;       // same trip count in every lane
+                        const unsigned rdiv = ((1u << 20) + (unsigned)R - 1u) / (unsigned)R;
+                        for (int it = 0; it < nit; ++it) {
+                            const int i = lane + 32 * it, ic = min(i, npr - 1);
+                            const int q = (int)(((unsigned)ic * rdiv) >> 20);
+                            const int gg = g0 + ic - q * R;
+                            const double w = weigh(s_gu[gg], s_gu[S2_ROWS + gg], s_gu[2 * S2_ROWS + gg], q,
+                                                   i < npr && q < nq && s_gvalid[gg] != 0);
+                            if (i < npr) gblk[q * G + gg] = w;
+                        }
+                    }
+                    if (lc == 0) npairs += (unsigned long long)npb;
+                    S2_TICK(7);
+                    // Gram matrix of the batch (members only: the pseudo-member column is masked): row n of the batch,
+                    // this lane's two members of every 8-member tile
                     {
                         double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+                        if (stage_rows) {
+                            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                            __syncwarp();
+                            const double *yrow = stg + n * YW + 2 * c;
 #pragma unroll
-                        for (int t = 0; t < NT3; ++t) {
-                            const double v1 = (t == NT3 - 1 && c == 3) ? 0.0 : yv[t].y;
-                            s2_dmma(g0, g1, yv[t].x, yv[t].x);
-                            s2_dmma(h0, h1, v1, v1);
+                            for (int t = 0; t < NT3; ++t) {
+                                const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t);
+                                const double v1 = (t == NT3 - 1 && c == 3) ? 0.0 : v.y;
+                                s2_dmma(g0, g1, v.x, v.x);
+                                s2_dmma(h0, h1, v1, v1);
+                            }
+                        } else {
+                            const int krow = __shfl_sync(0xffffffffu, cur.kk, n);
+                            const double *yrow = p.Yw + (size_t)(krow >= 0 ? krow : p.nobs) * YW + 2 * c;
+#pragma unroll
+                            for (int t = 0; t < NT3; ++t) {
+                                const double2 v = __ldg(reinterpret_cast<const double2 *>(yrow + 8 * t));
+                                const double v1 = (t == NT3 - 1 && c == 3) ? 0.0 : v.y;
+                                s2_dmma(g0, g1, v.x, v.x);
+                                s2_dmma(h0, h1, v1, v1);
+                            }
                         }
                         *reinterpret_cast<double2 *>(gblk + 8 * G + n * 8 + 2 * c) = make_double2(g0 + h0, g1 + h1);
                     }
+                    cur = nxt;
+                    S2_TICK(8);
                 }
+                S2_TICK(9);
             }
             // the blocks were written through the generic proxy and are read by bulk copies (async proxy)
+            // (and the ring, used as a generic-proxy staging area above, is written by them again)
             __threadfence();
             asm volatile("fence.proxy.async.global;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            S2_TICK(2);
             __syncthreads();
+            S2_TICK(5);
 
             // =============================== rows into registers ===============================
-            if (is_consumer) {
+            {
                 if (!loaded) {
                     double sum = 0.0;
 #pragma unroll
@@ -412,43 +486,47 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 }
             }
 
+            S2_TICK(3);
             // =============================== PHASE B ===============================
-            if (!is_consumer) {
-                // ---- issuer: per batch 8 row copies (lanes 0..7) + the block copy (lane 8) onto the stage's barrier
+            {
+                // Batch j of the chunk lives in ring stage (gbatch + j) % S.  Copies: 8 rows (lanes 0..7) + the block
+                // (lane 8) onto the stage's `full` barrier.  Who issues: the first min(S, nb) batches one per warp at
+                // the start; batch j >= S by warp (j - S + D) % 16 right after that warp has finished batch j - S + D
+                // (D = S/4): the stage was released D batches ago by every warp that is not lagging, so the wait on
+                // `empty` practically never blocks, and the copy has S - D batches of time to land.
                 constexpr unsigned ROW_BYTES = YW * sizeof(double);
                 const unsigned blk_bytes = (unsigned)BLK * sizeof(double);
-                for (int b = 0; b < nb; ++b) {
-                    s2_mbar_wait_empty(s_empty + rs, rpar ^ 1u);
-                    double *sy = s_ring + (size_t)rs * SD;
+                const int D = S >> 2;
+                auto issue = [&](int j) {
+                    const unsigned gbj = gbatch + (unsigned)j;
+                    const int st = (int)(gbj % (unsigned)S);
+                    const unsigned par = (gbj / (unsigned)S) & 1u;
+                    s2_mbar_wait_empty(s_empty + st, par ^ 1u);
+                    double *sy = s_ring + (size_t)st * SD;
                     if (lane < 8) {
-                        const int idx = 8 * b + lane;
+                        const int idx = 8 * j + lane;
                         const int64_t k = idx < ncand ? (int64_t)s_cand[idx] : p.nobs;       // past the end: the zero row
-                        s2_bulk_g2s(sy + lane * YST + (lane >> 1) * 4, p.Yw + (size_t)k * YW, ROW_BYTES, s_full + rs);
+                        s2_bulk_g2s(sy + lane * YST + (lane >> 1) * 4, p.Yw + (size_t)k * YW, ROW_BYTES, s_full + st);
                     } else if (lane == 8) {
-                        s2_bulk_g2s(sy + YD, blocks + (size_t)b * BLK, blk_bytes, s_full + rs);
+                        s2_bulk_g2s(sy + YD, blocks + (size_t)j * BLK, blk_bytes, s_full + st);
                     }
-                    if (lane == 0) s2_mbar_arrive_expect_tx(s_full + rs, 8u * ROW_BYTES + blk_bytes);
-                    rs = (rs + 1 == S) ? 0 : rs + 1;
-                    rpar ^= (rs == 0) ? 1u : 0u;
-                }
-            } else {
-                // ---- consumers
+                    if (lane == 0) s2_mbar_arrive_expect_tx(s_full + st, 8u * ROW_BYTES + blk_bytes);
+                };
+                if (warp < S && warp < nb) issue(warp);
+                int rs = (int)(gbatch % (unsigned)S);
+                unsigned rpar = (gbatch / (unsigned)S) & 1u;
                 for (int b = 0; b < nb; ++b) {
                     s2_mbar_wait_full(s_full + rs, rpar);
                     const double *sy = s_ring + (size_t)rs * SD;
                     const double *som = sy + YD;
                     const double *Gb = som + 8 * G;
 
-                    // omega of this row's grid point for the 8 obs of the batch
+                    // omega of this row's grid point for the 8 obs of the batch (ob-major block: om[q][G])
                     double om[8];
-                    {
-                        const double2 *po = reinterpret_cast<const double2 *>(som + gslot * 8);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const double2 v = po[i];
-                            om[2 * i] = active ? v.x : 0.0;
-                            om[2 * i + 1] = active ? v.y : 0.0;
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const double v = som[i * G + gslot];
+                        om[i] = active ? v : 0.0;
                     }
                     // any weight non-zero?  (integer test of the bit patterns: the FP64 pipe is the contended one)
                     long long anyb = 0;
@@ -456,8 +534,9 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     for (int i = 0; i < 8; ++i) anyb |= __double_as_longlong(om[i]);
                     const bool any = (anyb << 1) != 0;
                     if (__any_sync(0xffffffffu, any)) {
-                        // step 1: g[row][ob] = x[row] . y_ob  (two accumulator chains)
-                        double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
+                        // step 1: g[row][ob] = x[row] . y_ob   (one accumulator chain: four warps per sub-partition keep
+                        // the pipe fed, and the two halves need not be added afterwards)
+                        double ga0 = 0.0, ga1 = 0.0;
                         {
                             const double *yrow = sy + n * YST + (n >> 1) * 4 + 2 * c;     // B operand: ob = n, members of lane c
 #pragma unroll
@@ -465,22 +544,15 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                                 const double2 v = *reinterpret_cast<const double2 *>(yrow + 8 * t);
                                 const double a1 = (t == NT3 - 1 && c == 3) ? 0.0 : x[2 * t + 1];   // mask the mean
                                 s2_dmma(ga0, ga1, x[2 * t], v.x);
-                                s2_dmma(gb0, gb1, a1, v.y);
+                                s2_dmma(ga0, ga1, a1, v.y);
                             }
                         }
-                        ga0 += gb0;                                            // g[row][2c]
-                        ga1 += gb1;                                            // g[row][2c+1]
-                        // all-gather the 8 dots of the row over its 4 lanes
+                        // lane c of a row holds g[row][2c], g[row][2c+1]: obs 0..3 are broadcast to the row's 4 lanes now,
+                        // obs 4..7 after their correction by obs 0..3 below
                         double gq[8];
-                        {
-                            const double o0 = __shfl_xor_sync(0xffffffffu, ga0, 1), o1 = __shfl_xor_sync(0xffffffffu, ga1, 1);
-                            double q0, q1, q2, q3;
-                            if (c & 1) { q0 = o0; q1 = o1; q2 = ga0; q3 = ga1; } else { q0 = ga0; q1 = ga1; q2 = o0; q3 = o1; }
-                            const double r0 = __shfl_xor_sync(0xffffffffu, q0, 2), r1 = __shfl_xor_sync(0xffffffffu, q1, 2);
-                            const double r2 = __shfl_xor_sync(0xffffffffu, q2, 2), r3 = __shfl_xor_sync(0xffffffffu, q3, 2);
-                            if (c & 2) { gq[0] = r0; gq[1] = r1; gq[2] = r2; gq[3] = r3; gq[4] = q0; gq[5] = q1; gq[6] = q2; gq[7] = q3; }
-                            else { gq[0] = q0; gq[1] = q1; gq[2] = q2; gq[3] = q3; gq[4] = r0; gq[5] = r1; gq[6] = r2; gq[7] = r3; }
-                        }
+                        const int l0r = lane & ~3;
+                        gq[0] = __shfl_sync(0xffffffffu, ga0, l0r); gq[1] = __shfl_sync(0xffffffffu, ga1, l0r);
+                        gq[2] = __shfl_sync(0xffffffffu, ga0, l0r + 1); gq[3] = __shfl_sync(0xffffffffu, ga1, l0r + 1);
                         // step 2: the serial recurrence inside the batch (per row; every lane of the row computes it)
                         double e[8];
                         e[0] = om[0] * gq[0];
@@ -488,13 +560,14 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                         e[2] = om[2] * (gq[2] - Gb[16] * e[0] - Gb[17] * e[1]);
                         e[3] = om[3] * (gq[3] - Gb[24] * e[0] - Gb[25] * e[1] - Gb[26] * e[2]);
                         {
-                            // obs 4..7 see obs 0..3 through one more 8x8x4 product: corr[row][q] = sum_p e_p G[4+q][p]
-                            const double ea = (c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3];
-                            double k0 = 0.0, k1 = 0.0;
-                            s2_dmma(k0, k1, ea, Gb[(4 + (n & 3)) * 8 + c]);
-                            const double o0 = __shfl_xor_sync(0xffffffffu, k0, 1), o1 = __shfl_xor_sync(0xffffffffu, k1, 1);
-                            if (c & 1) { gq[4] -= o0; gq[5] -= o1; gq[6] -= k0; gq[7] -= k1; }
-                            else { gq[4] -= k0; gq[5] -= k1; gq[6] -= o0; gq[7] -= o1; }
+                            // obs 4..7 see obs 0..3 through one more 8x8x4 product on top of their own dots: the
+                            // accumulator starts from g (lanes c = 2, 3 hold g[row][4..7] in fragment layout), A = -e,
+                            // B[k][j] = G[j][k] for the columns j = 4..7
+                            const double ea = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
+                            double k0 = ga0, k1 = ga1;
+                            s2_dmma(k0, k1, ea, (n >= 4) ? Gb[n * 8 + c] : 0.0);
+                            gq[4] = __shfl_sync(0xffffffffu, k0, l0r + 2); gq[5] = __shfl_sync(0xffffffffu, k1, l0r + 2);
+                            gq[6] = __shfl_sync(0xffffffffu, k0, l0r + 3); gq[7] = __shfl_sync(0xffffffffu, k1, l0r + 3);
                         }
                         e[4] = om[4] * gq[4];
                         e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
@@ -520,14 +593,20 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     if (lane == 0) s2_mbar_arrive(s_empty + rs);
                     rs = (rs + 1 == S) ? 0 : rs + 1;
                     rpar ^= (rs == 0) ? 1u : 0u;
+                    // this warp's turn to refill a stage?
+                    const int j = b - D + S;
+                    if (b >= D && j < nb && ((b - D) & (S2_NW - 1)) == warp) issue(j);
                 }
+                gbatch += (unsigned)nb;
             }
+            S2_TICK(4);
             if (pos >= le) break;
             __syncthreads();                      // phase B is over before the next chunk's scan rewrites s_cand
+            S2_TICK(5);
         }
 
         // ---- write the patch back: xam of the row (ensrf.py:130) lives in lane c = 3 ---------------------------
-        if (is_consumer && loaded) {
+        if (loaded) {
             double mean = __shfl_sync(0xffffffffu, x[2 * NT3 - 1], (lane & ~3) | 3);
             if (!fused) mean = 0.0;
             if (active && dirty) {
@@ -542,6 +621,11 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 }
             }
         }
+    }
+    if (p.prof && tid == 0) {
+        S2_TICK(3);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) atomicAdd(&p.prof[i], (unsigned long long)pacc[i]);
     }
     if (p.counters) {
 #pragma unroll
@@ -647,9 +731,27 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st) {
         sweep_rows_kernel<TS><<<(unsigned)(p.nobs + 1), 128, 0, st>>>(Yp, p.rec, p.nobs, p.nens, YW, Yw);
         p.Yw = Yw; p.scratch = scratch; p.ticket = ticket;
         p.abort_flag = exb_status_slot_last_dev();
+        unsigned long long *prof = nullptr;
+        if (getenv("EXB_S2_PROF") && atoi(getenv("EXB_S2_PROF"))) {       // debugging aid: per-phase clocks of warp 0
+            if (cudaMalloc(&prof, 10 * sizeof(unsigned long long)) == cudaSuccess) cudaMemsetAsync(prof, 0, 10 * sizeof(unsigned long long), st);
+            else prof = nullptr;
+        }
+        p.prof = prof;
         state_sweep_2p_kernel<NT3, TS><<<(unsigned)grid, S2_NT, smem, st>>>(p);
         exb_count_launches(2);
         rc = exb_check_launch("state_sweep_2p_kernel");
+        if (prof) {
+            unsigned long long h[10];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaFree(prof);
+            double tot = 0;
+            for (int i = 0; i < 6; ++i) tot += (double)h[i];
+            for (int i = 6; i < 10; ++i) tot += (double)h[i];
+            fprintf(stderr, "[s2 prof] grid %d patches %d: setup %.1f%% scan %.1f%% park+fence %.1f%% rows %.1f%% phaseB %.1f%% barriers %.1f%% | blocks: scalars+staging %.1f%% omega %.1f%% gram %.1f%% rest %.1f%%  (%.3e clk per CTA)\n",
+                    grid, p.npatches, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot,
+                    100 * h[6] / tot, 100 * h[7] / tot, 100 * h[8] / tot, 100 * h[9] / tot, tot / grid);
+        }
     }
     if (Yw) cudaFreeAsync(Yw, st);
     if (scratch) cudaFreeAsync(scratch, st);

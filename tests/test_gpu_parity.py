@@ -796,14 +796,14 @@ def test_single_point_efa_demo_matches_notebook_arithmetic(obs_range, ob_error, 
     order = np.random.default_rng(8).permutation(n)
     got = enkf(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order)
     want = enkf_numpy(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order)
-    np.testing.assert_allclose(got, want, rtol=1e-12)
+    np.testing.assert_allclose(got, want, rtol=1e-11)
     assert np.abs(want - prior).max() > 0.1
     # the notebook shuffles the obs on every call; its variance (ddof 0) and covariance (ddof 1) normalisations differ
     # (cell 11, lines 64 and 75), so the result depends on the order even without localisation: check a second order
     order2 = order[::-1].copy()
     np.testing.assert_allclose(enkf(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order2),
                                enkf_numpy(obs, prior, obs_range=obs_range, ob_error=ob_error, inflation=inflation, order=order2),
-                               rtol=1e-12)
+                               rtol=1e-11)
 
 
 def test_one_dimensional_latlon_state_matches_reference_golden():
