@@ -287,7 +287,13 @@ def run_ours(args):
     ny, nx, nens = cfg['ny'], cfg['nx'], cfg['nmem']
     nrows = nlev * ny * nx
     # the host-resident state has the storage type of the run (float32 runs: float32 storage, float64 arithmetic)
-    Xh = torch.empty((nrows, nens), dtype=tdtype).pin_memory()
+    state_gb_host = nrows * nens * esize / 2 ** 30
+    if not host_mem_ok(3.0 * state_gb_host + 8):
+        raise SystemExit('bench.py: not enough host RAM for a %.1f GB state' % state_gb_host)
+    if not args.no_e2e and not host_mem_ok(4.0 * state_gb_host + 8):
+        args.no_e2e = True                      # the end-to-end leg needs a second page-locked copy of the state
+        print('bench.py: skipping the e2e leg (host RAM)', file=sys.stderr)
+    Xh = torch.empty((nrows, nens), dtype=tdtype, pin_memory=True)
     case, _ = build_case(args, out=Xh.numpy().reshape(cfg['nvars'], cfg['ntimes'], ny, nx, nens))
     obs = obs_arrays(case)
     nassim = int(obs.assimilate.sum())
@@ -363,10 +369,10 @@ def run_ours(args):
         # host-resident state: at N = 1 one pinned buffer; at N > 1 sharded by latitude bands, every rank holds,
         # uploads and downloads its own band (pinned) over its own PCIe link
         if world == 1:
-            Xh_in, Oh = Xh, torch.empty_like(Xh).pin_memory()
+            Xh_in, Oh = Xh, torch.empty(Xh.shape, dtype=Xh.dtype, pin_memory=True)
         else:
             Xh_in = sharding.band_view(Xh, nlev, ny, nx, y0, y1).contiguous().reshape(-1, nens).pin_memory()
-            Oh = torch.empty_like(Xh_in).pin_memory()
+            Oh = torch.empty(Xh_in.shape, dtype=Xh_in.dtype, pin_memory=True)
 
         def e2e_step():
             return engine.analysis_host(Xh_in, nlev, case.lat2d, case.lon2d, obs, loc_mode, device=dev, dtype=tdtype,

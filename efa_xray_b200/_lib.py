@@ -48,6 +48,10 @@ SIGNATURES = {
     'exb_state_update_f32': [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p],
     'exb_state_sweep_f64': [_p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p],
     'exb_state_sweep_f32': [_p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p],
+    'exb_sweep_plan_create': [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p],
+    'exb_sweep_plan_destroy': [_p],
+    'exb_state_sweep_planned_f64': [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p],
+    'exb_state_sweep_planned_f32': [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p],
     'exb_localization_weights': [_p, _i64, _dbl, _dbl, _dbl, _int, _p, _p, _p],
     'exb_gaspari_cohn': [_p, _i64, _dbl, _p, _p],
     'exb_ensrf_host_f64': [_p, _i64, _i64, _i64, _int, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,

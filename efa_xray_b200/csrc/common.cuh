@@ -156,30 +156,50 @@ __device__ __forceinline__ double loc_weight_fast_t(double a, double inv_hw, dou
 // Lean form for warp-convergent callers (every lane of the warp must call it): the same arithmetic with the
 // special-function seeds taken in double format (MUFU.RSQ64H / RCP64H: no conversions, no libm fix-up code), no
 // clamps (values outside the support may become Inf/NaN on the way and are discarded by the final SELECT), and only
-// the Gaspari-Cohn branch the warp needs when all of its lanes fall on the same side of r = 1.
+// the Gaspari-Cohn branch the warp needs when all of its lanes fall on the same side of r = 1.  The constants that are
+// not exact in 32 bits come from a table in the kernel's parameter block (one uniform load each; as literals every
+// use costs two moves): k.q = series coefficients c0..c19, k.g = {5/3, 1/12, 2/3, 2 R_earth}.
+struct ExbLocConst { double q[20]; double g[4]; };
+static inline ExbLocConst exb_loc_const() {
+    ExbLocConst k;
+    const double c[20] = {1.0, 0.16666666666666666, 0.075, 0.044642857142857144, 0.030381944444444444, 0.022372159090909092,
+                          0.017352764423076924, 0.01396484375, 0.011551800896139705, 0.009761609529194078,
+                          0.008390335809616815, 0.0073125258735988454, 0.006447210311889649, 0.005740037670841924,
+                          0.005153309682319905, 0.004660143486915096, 0.004240907093679363, 0.003880964558837669,
+                          0.0035692053938259347, 0.003297059503473485};
+    for (int i = 0; i < 20; ++i) k.q[i] = c[i];
+    k.g[0] = 5.0 / 3.0; k.g[1] = 1.0 / 12.0; k.g[2] = 2.0 / 3.0; k.g[3] = 2.0 * EXB_R_EARTH;
+    return k;
+}
 template <bool SHORT>
-__device__ __forceinline__ double loc_weight_lean(double a, double inv_hw, double a_max) {
+__device__ __forceinline__ double loc_weight_lean(const ExbLocConst &k, double a, double inv_hw, double a_max) {
     const double ap = a + 1e-300;                              // a = 0 (ob on a grid point): r = 0, weight 1
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ap));    // ~2^-22
     const double hm = -0.5 * ap;
     y = y * fma(hm, y * y, 1.5);
     y = y * fma(hm, y * y, 1.5);
-    const double q = SHORT ? exb_asin_sqrt_over_sqrt_short(a) : exb_asin_sqrt_over_sqrt(a);
-    const double r = ((2.0 * EXB_R_EARTH) * inv_hw) * ((ap * y) * q);
+    // asin(sqrt(a)) / sqrt(a) = sum c_n a^n, Horner on two interleaved halves (see exb_asin_sqrt_over_sqrt)
+    const double a2 = a * a;
+    constexpr int NQ = SHORT ? 10 : 20;
+    double pe = k.q[NQ - 2], po = k.q[NQ - 1];
+#pragma unroll
+    for (int i = NQ - 4; i >= 0; i -= 2) { pe = fma(pe, a2, k.q[i]); po = fma(po, a2, k.q[i + 1]); }
+    const double q = fma(po, a, pe);
+    const double r = (k.g[3] * inv_hw) * ((ap * y) * q);
     const bool inner = r <= 1.0;
     double w;
     if (__all_sync(0xffffffffu, inner)) {
-        w = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+        w = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -k.g[0]), r * r, 1.0);
     } else {
         double ir;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ir) : "d"(r));
         ir = ir * fma(-r, ir, 2.0);
         ir = ir * fma(-r, ir, 2.0);
-        const double p2 = fma(fma(fma(fma(fma(r, 1.0 / 12.0, -0.5), r, 0.625), r, 5.0 / 3.0), r, -5.0), r, 4.0) - (2.0 / 3.0) * ir;
+        const double p2 = fma(fma(fma(fma(fma(r, k.g[1], -0.5), r, 0.625), r, k.g[0]), r, -5.0), r, 4.0) - k.g[2] * ir;
         w = (r < 2.0) ? p2 : 0.0;
         if (__any_sync(0xffffffffu, inner)) {
-            const double p1 = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -5.0 / 3.0), r * r, 1.0);
+            const double p1 = fma(fma(fma(fma(-0.25, r, 0.5), r, 0.625), r, -k.g[0]), r * r, 1.0);
             w = inner ? p1 : w;
         }
     }
@@ -212,6 +232,20 @@ struct SweepLists {
     int *list = nullptr;
     const int64_t *tile_off = nullptr;    // off shifted so that it is indexed by absolute coarse-tile number
     int nctx = 1, eq_row = -1;
+};
+// Geometry-only part of a state sweep, built ahead of the obs-space solve (exb_sweep_plan_create): the fp32 scan
+// records of the obs and the candidate lists per coarse tile for the patch shape of the two-phase kernel.
+struct ExbSweepPlan {
+    int64_t nlev = 0, ny = 0, nx = 0, nobs = 0, ob_begin = 0, ob_end = 0, y_begin = 0, y_end = 0;
+    int loc_mode = 0, bty = 0, btx = 0;
+    const double *grid_u = nullptr;       // identity of the inputs the plan was built from
+    const double *obgeo = nullptr;
+    float4 *scan = nullptr;
+    bool have_lists = false;
+    SweepLists lists;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ready = nullptr, used = nullptr;
+    bool was_used = false;
 };
 bool sweep_lists_wanted(int loc_mode, int64_t ob_begin, int64_t ob_end);
 int sweep_build_lists(const double *grid_u, int64_t npts, int nx, int y_begin, int y_end, int bty, int btx, const float4 *scan,

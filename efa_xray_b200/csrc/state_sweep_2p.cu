@@ -67,6 +67,7 @@ struct S2Params {
     int G, Lc, nlc;
     int loc_mode;
     int nstages, stage_doubles, blk_doubles, npatches;
+    ExbLocConst kloc;                 // constants of the localisation weight (parameter block = constant bank)
 };
 
 __device__ __forceinline__ void s2_dmma(double &c0, double &c1, double a, double b) {
@@ -110,6 +111,23 @@ __device__ __forceinline__ void s2_mbar_wait_empty(unsigned long long *bar, unsi
 __device__ __forceinline__ void s2_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(s2_smem(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(s2_smem(bar)) : "memory");
+}
+
+// v[c] for a lane-dependent c in 0..3 as three predicated selects (written with ternaries the compiler emits divergent
+// branches here, which serialise the four lanes of every row)
+__device__ __forceinline__ double s2_sel4(double v0, double v1, double v2, double v3, int c) {
+    double lo, hi, r;
+    asm("{\n.reg .pred p, q;\nsetp.ne.s32 p, %3, 0;\nsetp.ne.s32 q, %4, 0;\n"
+        "selp.f64 %0, %6, %5, p;\nselp.f64 %1, %8, %7, p;\nselp.f64 %2, %1, %0, q;\n}\n"
+        : "=&d"(lo), "=&d"(hi), "=d"(r) : "r"(c & 1), "r"(c & 2), "d"(v0), "d"(v1), "d"(v2), "d"(v3));
+    return r;
+}
+
+// read-only global load the compiler may not sink towards its use (prefetches one batch ahead stay where they are)
+__device__ __forceinline__ double s2_ldg_now(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+    return v;
 }
 
 template <int NT3> __host__ __device__ constexpr int s2_yst() { return ((8 * NT3) % 16 == 8) ? 8 * NT3 : 8 * NT3 + 8; }
@@ -319,18 +337,19 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 double *stg = s_ring + (size_t)warp * (8 * YW);
                 const bool stage_rows = (size_t)S2_NW * 8 * YW <= (size_t)S * SD;
                 // scalars of the obs of a batch, held by lanes 0..7; loaded one batch ahead
-                struct ObSc { double ux, uy, uz, ihw, amax, cb; int kk; };
+                struct ObSc { double ux, uy, uz, ihw, amax, c1, beta; int kk; };      // (no arithmetic on the loaded values
+                                                                                     // here: it would wait for them)
                 auto load_sc = [&](int b, ObSc &o) {
-                    o.ux = o.uy = o.uz = o.ihw = o.amax = o.cb = 0.0;
+                    o.ux = o.uy = o.uz = o.ihw = o.amax = o.c1 = o.beta = 0.0;
                     o.kk = -1;
                     if (b < nb && lane < 8 && 8 * b + lane < ncand) {
                         const int kk = s_cand[8 * b + lane];
                         o.kk = kk;
-                        o.ux = __ldg(p.geo + GEO_UX * p.nobs + kk); o.uy = __ldg(p.geo + GEO_UY * p.nobs + kk);
-                        o.uz = __ldg(p.geo + GEO_UZ * p.nobs + kk); o.ihw = __ldg(p.geo + GEO_INVHW * p.nobs + kk);
-                        o.amax = __ldg(p.geo + GEO_AMAX * p.nobs + kk);
-                        // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it
-                        o.cb = __ldg(p.rec + REC_C1 * p.nobs + kk) * __ldg(p.rec + REC_BETA * p.nobs + kk);
+                        o.ux = s2_ldg_now(p.geo + GEO_UX * p.nobs + kk); o.uy = s2_ldg_now(p.geo + GEO_UY * p.nobs + kk);
+                        o.uz = s2_ldg_now(p.geo + GEO_UZ * p.nobs + kk); o.ihw = s2_ldg_now(p.geo + GEO_INVHW * p.nobs + kk);
+                        o.amax = s2_ldg_now(p.geo + GEO_AMAX * p.nobs + kk);
+                        o.c1 = s2_ldg_now(p.rec + REC_C1 * p.nobs + kk);
+                        o.beta = s2_ldg_now(p.rec + REC_BETA * p.nobs + kk);
                     }
                 };
                 ObSc cur, nxt;
@@ -342,7 +361,8 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     if (lane < 8) {          // per ob: ux uy uz 1/halfwidth a_max beta*c1
                         *reinterpret_cast<double2 *>(sob + 6 * lane) = make_double2(cur.ux, cur.uy);
                         *reinterpret_cast<double2 *>(sob + 6 * lane + 2) = make_double2(cur.uz, cur.ihw);
-                        *reinterpret_cast<double2 *>(sob + 6 * lane + 4) = make_double2(cur.amax, cur.cb);
+                        // beta / ((N-1) kdenom)   (ensrf.py:95, :119, :135-136); the localisation weight multiplies it
+                        *reinterpret_cast<double2 *>(sob + 6 * lane + 4) = make_double2(cur.amax, cur.c1 * cur.beta);
                     }
                     if (stage_rows) {
                         // 8 rows x YW doubles = 8 * YW / 2 chunks of 16 bytes, dealt to the lanes
@@ -375,8 +395,8 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                         double w = 1.0;
                         if (p.loc_mode == EXB_LOC_GC) {
                             const double a = hav_a(gx, gy, gz, o01.x, o01.y, o23.x);
-                            w = shortser ? loc_weight_lean<true>(a, o23.y, o45.x)
-                                : fast   ? loc_weight_lean<false>(a, o23.y, o45.x)
+                            w = shortser ? loc_weight_lean<true>(p.kloc, a, o23.y, o45.x)
+                                : fast   ? loc_weight_lean<false>(p.kloc, a, o23.y, o45.x)
                                          : loc_weight(a, o23.y, o45.x);
                         }
                         w = valid ? w : 0.0;
@@ -559,11 +579,11 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                         e[1] = om[1] * (gq[1] - Gb[8] * e[0]);
                         e[2] = om[2] * (gq[2] - Gb[16] * e[0] - Gb[17] * e[1]);
                         e[3] = om[3] * (gq[3] - Gb[24] * e[0] - Gb[25] * e[1] - Gb[26] * e[2]);
+                        const double ea = -s2_sel4(e[0], e[1], e[2], e[3], c);     // -e[c]: A operand below and in step 3
                         {
                             // obs 4..7 see obs 0..3 through one more 8x8x4 product on top of their own dots: the
                             // accumulator starts from g (lanes c = 2, 3 hold g[row][4..7] in fragment layout), A = -e,
                             // B[k][j] = G[j][k] for the columns j = 4..7
-                            const double ea = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
                             double k0 = ga0, k1 = ga1;
                             s2_dmma(k0, k1, ea, (n >= 4) ? Gb[n * 8 + c] : 0.0);
                             gq[4] = __shfl_sync(0xffffffffu, k0, l0r + 2); gq[5] = __shfl_sync(0xffffffffu, k1, l0r + 2);
@@ -573,8 +593,8 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                         e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
                         e[6] = om[6] * (gq[6] - Gb[52] * e[4] - Gb[53] * e[5]);
                         e[7] = om[7] * (gq[7] - Gb[60] * e[4] - Gb[61] * e[5] - Gb[62] * e[6]);
-                        const double ea0 = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
-                        const double ea1 = -((c == 0) ? e[4] : (c == 1) ? e[5] : (c == 2) ? e[6] : e[7]);
+                        const double ea0 = ea;                 // A operand of the first k-step: -e[c]
+                        const double ea1 = -s2_sel4(e[4], e[5], e[6], e[7], c);
 
                         // step 3: x[row][:] -= sum_q e_q y_q[:]   (A = -e in two k-steps, B = y, C = x)
                         {
@@ -667,7 +687,7 @@ void s2_patch_shape(int64_t nlev, int64_t ny, int64_t nx, int *Lc_out, int *bty_
 }
 
 template <int NT3, typename TS>
-static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st) {
+static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepPlan *plan) {
     int Lc, bty, btx;
     s2_patch_shape(p.nlev, p.ny, p.nx, &Lc, &bty, &btx);
     p.ty = bty; p.tx = btx; p.G = bty * btx; p.Lc = Lc;
@@ -706,7 +726,14 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st) {
     p.tile_off = nullptr;
     p.tile_list = nullptr;
     p.nctx = 1;
-    if (sweep_lists_wanted(p.loc_mode, p.ob_begin, p.ob_end)) {
+    if (plan && plan->have_lists && plan->bty == bty && plan->btx == btx && plan->y_begin <= p.y_begin && p.y_end <= plan->y_end &&
+        plan->ob_begin == p.ob_begin && plan->ob_end == p.ob_end) {
+        // lists built ahead (exb_sweep_plan_create): indexed by absolute coarse tile, so they serve any row sub-range
+        p.nctx = plan->lists.nctx;
+        p.pr_eq = plan->lists.eq_row / bty;
+        p.tile_off = plan->lists.tile_off;
+        p.tile_list = plan->lists.list;
+    } else if (sweep_lists_wanted(p.loc_mode, p.ob_begin, p.ob_end)) {
         const int rcl = sweep_build_lists(p.grid_u, p.npts, p.nx, p.y_begin, p.y_end, bty, btx, p.scan, p.ob_begin, p.ob_end, st, &lists);
         if (rcl != EXB_OK) { sweep_free_lists(lists, st); return rcl; }
         p.nctx = lists.nctx;
@@ -768,24 +795,25 @@ template <typename TS>
 int exb_state_sweep_2p(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
                        const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
                        int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
-                       cudaStream_t st) {
+                       cudaStream_t st, const ExbSweepPlan *plan) {
     S2Params p;
     memset(&p, 0, sizeof(p));
     p.xm = xm; p.Xp = Xp; p.grid_u = grid_u; p.rec = rec; p.geo = obgeo; p.scan = scan;
     p.counters = counters; p.npts = ny * nx; p.nobs = nobs; p.ob_begin = ob_begin; p.ob_end = ob_end;
     p.nlev = (int)nlev; p.ny = (int)ny; p.nx = (int)nx; p.nens = nens; p.loc_mode = loc_mode;
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
+    p.kloc = exb_loc_const();
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
-    if (need <= 4) return s2_launch<4, TS>(p, Yp, st);
-    if (need <= 7) return s2_launch<7, TS>(p, Yp, st);
-    if (need <= 10) return s2_launch<10, TS>(p, Yp, st);
-    if (need <= 13) return s2_launch<13, TS>(p, Yp, st);
+    if (need <= 4) return s2_launch<4, TS>(p, Yp, st, plan);
+    if (need <= 7) return s2_launch<7, TS>(p, Yp, st, plan);
+    if (need <= 10) return s2_launch<10, TS>(p, Yp, st, plan);
+    if (need <= 13) return s2_launch<13, TS>(p, Yp, st, plan);
     return EXB_ERR_UNSUPPORTED;                       // larger ensembles: state_update_mma.cu / state_update.cu
 }
 
 template int exb_state_sweep_2p<double>(double *, double *, int64_t, int64_t, int64_t, int, const double *, const double *,
                                         const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
-                                        int64_t, int, unsigned long long *, cudaStream_t);
+                                        int64_t, int, unsigned long long *, cudaStream_t, const ExbSweepPlan *);
 template int exb_state_sweep_2p<float>(float *, float *, int64_t, int64_t, int64_t, int, const double *, const float *,
                                        const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
-                                       int64_t, int, unsigned long long *, cudaStream_t);
+                                       int64_t, int, unsigned long long *, cudaStream_t, const ExbSweepPlan *);

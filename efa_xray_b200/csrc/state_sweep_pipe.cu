@@ -865,7 +865,7 @@ template <typename TS>
 int exb_state_sweep_2p(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
                        const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
                        int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
-                       cudaStream_t st);
+                       cudaStream_t st, const ExbSweepPlan *plan);
 void s2_patch_shape(int64_t nlev, int64_t ny, int64_t nx, int *Lc_out, int *bty_out, int *btx_out);
 
 // EXB_SP_IMPL = 2p (default: two-phase kernel, state_sweep_2p.cu) | v3 (the concurrent producer/consumer kernel above)
@@ -901,10 +901,10 @@ template <typename TS>
 int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
                          const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
                          int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
-                         cudaStream_t st) {
+                         cudaStream_t st, const ExbSweepPlan *plan) {
     if (sp_use_2p()) {
         const int rc = exb_state_sweep_2p<TS>(xm, Xp, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, scan, nobs, ob_begin, ob_end,
-                                              y_begin, y_end, loc_mode, counters, st);
+                                              y_begin, y_end, loc_mode, counters, st, plan);
         if (rc != EXB_ERR_UNSUPPORTED) return rc;
     }
     SpParams p;
@@ -938,7 +938,69 @@ int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, i
 
 template int exb_state_sweep_pipe<double>(double *, double *, int64_t, int64_t, int64_t, int, const double *, const double *,
                                           const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
-                                          int64_t, int, unsigned long long *, cudaStream_t);
+                                          int64_t, int, unsigned long long *, cudaStream_t, const ExbSweepPlan *);
 template int exb_state_sweep_pipe<float>(float *, float *, int64_t, int64_t, int64_t, int, const double *, const float *,
                                          const double *, const double *, const float4 *, int64_t, int64_t, int64_t, int64_t,
-                                         int64_t, int, unsigned long long *, cudaStream_t);
+                                         int64_t, int, unsigned long long *, cudaStream_t, const ExbSweepPlan *);
+
+// ------------------------------------------------------------------------------------------
+// sweep plan: the geometry-only part of the sweep, built ahead of the obs-space solve
+// ------------------------------------------------------------------------------------------
+__global__ void sweep_scan_from_flags_kernel(const double *__restrict__ geo, const uint8_t *__restrict__ assim, int64_t nobs,
+                                             float4 *__restrict__ scan) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nobs) return;
+    float4 v;
+    v.x = (float)geo[GEO_UX * nobs + k];
+    v.y = (float)geo[GEO_UY * nobs + k];
+    v.z = (float)geo[GEO_UZ * nobs + k];
+    // same record as su_scan_records_kernel (state_update.cu) builds from rec[REC_ASSIM] after the solve
+    v.w = assim[k] ? (float)geo[GEO_THETA * nobs + k] * 1.000001f + 1e-7f : -1.f;
+    scan[k] = v;
+}
+
+static void sweep_plan_free(ExbSweepPlan *pl) {
+    if (!pl) return;
+    if (pl->was_used && pl->used) cudaStreamWaitEvent(pl->st, pl->used, 0);
+    if (pl->scan) cudaFreeAsync(pl->scan, pl->st);
+    sweep_free_lists(pl->lists, pl->st);
+    if (pl->ready) cudaEventDestroy(pl->ready);
+    if (pl->used) cudaEventDestroy(pl->used);
+    delete pl;
+}
+
+extern "C" int exb_sweep_plan_create(const double *grid_u, int64_t nlev, int64_t ny, int64_t nx, const double *obgeo,
+                                     const uint8_t *ob_assimilate, int64_t nobs, int64_t ob_begin, int64_t ob_end,
+                                     int64_t y_begin, int64_t y_end, int loc_mode, void *stream, void **plan) {
+    EXB_REQUIRE(grid_u && obgeo && ob_assimilate && plan, "null pointer");
+    EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nobs > 0, "bad sizes");
+    EXB_REQUIRE(0 <= ob_begin && ob_begin <= ob_end && ob_end <= nobs && 0 <= y_begin && y_begin < y_end && y_end <= ny, "bad ranges");
+    *plan = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    ExbSweepPlan *pl = new ExbSweepPlan();
+    struct Guard { ExbSweepPlan *p; ~Guard() { if (p) sweep_plan_free(p); } } guard{pl};
+    pl->nlev = nlev; pl->ny = ny; pl->nx = nx; pl->nobs = nobs; pl->ob_begin = ob_begin; pl->ob_end = ob_end;
+    pl->y_begin = y_begin; pl->y_end = y_end; pl->loc_mode = loc_mode; pl->grid_u = grid_u; pl->obgeo = obgeo; pl->st = st;
+    EXB_CUDA(cudaEventCreateWithFlags(&pl->ready, cudaEventDisableTiming));
+    EXB_CUDA(cudaEventCreateWithFlags(&pl->used, cudaEventDisableTiming));
+    EXB_CUDA(exb_malloc_async(&pl->scan, (size_t)nobs * sizeof(float4), st));
+    sweep_scan_from_flags_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, ob_assimilate, nobs, pl->scan);
+    exb_count_launches(1);
+    if (sp_use_2p() && sweep_lists_wanted(loc_mode, ob_begin, ob_end)) {
+        int Lc;
+        s2_patch_shape(nlev, ny, nx, &Lc, &pl->bty, &pl->btx);
+        const int rc = sweep_build_lists(grid_u, ny * nx, (int)nx, (int)y_begin, (int)y_end, pl->bty, pl->btx, pl->scan, ob_begin,
+                                         ob_end, st, &pl->lists);
+        if (rc != EXB_OK) return rc;
+        pl->have_lists = true;
+    }
+    EXB_CUDA(cudaEventRecord(pl->ready, st));
+    guard.p = nullptr;
+    *plan = pl;
+    return exb_check_launch("sweep_scan_from_flags_kernel");
+}
+
+extern "C" int exb_sweep_plan_destroy(void *plan) {
+    sweep_plan_free(static_cast<ExbSweepPlan *>(plan));
+    return EXB_OK;
+}

@@ -28,7 +28,7 @@ template <typename TS>
 int exb_state_sweep_pipe(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const TS *Yp,
                          const double *rec, const double *obgeo, const float4 *scan, int64_t nobs, int64_t ob_begin,
                          int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
-                         cudaStream_t st);
+                         cudaStream_t st, const ExbSweepPlan *plan = nullptr);
 
 #define SU_NT 256
 #define SU_QCAP 16
@@ -405,7 +405,8 @@ extern "C" int exb_state_update_f32(float *xm, float *Xp, int64_t nlev, int64_t 
 template <typename T>
 static int state_sweep_impl(T *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u, const T *Yp,
                             const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin, int64_t ob_end,
-                            int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters, void *stream) {
+                            int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters, void *stream,
+                            ExbSweepPlan *plan = nullptr) {
     EXB_REQUIRE(X && grid_u && Yp && rec && obgeo, "null pointer");
     EXB_REQUIRE(nlev > 0 && ny > 0 && nx > 0 && nens >= 2 && nobs > 0, "bad sizes");
     EXB_REQUIRE(nlev < (1 << 30) && ny < (1 << 30) && nx < (1 << 30), "dimension too large");
@@ -414,6 +415,20 @@ static int state_sweep_impl(T *X, int64_t nlev, int64_t ny, int64_t nx, int nens
     EXB_REQUIRE(loc_mode == EXB_LOC_NONE || loc_mode == EXB_LOC_GC, "bad loc_mode");
     if (ob_begin == ob_end || y_begin == y_end) return EXB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (plan) {
+        // scan records and candidate lists were built ahead, from the same geometry and assimilate flags
+        if (plan->nlev != nlev || plan->ny != ny || plan->nx != nx || plan->nobs != nobs || plan->loc_mode != loc_mode ||
+            plan->grid_u != grid_u || plan->obgeo != obgeo) {
+            exb_set_error("exb_state_sweep_planned: the plan was built for another grid / observation set");
+            return EXB_ERR_ARG;
+        }
+        EXB_CUDA(cudaStreamWaitEvent(st, plan->ready, 0));
+        const int rc = exb_state_sweep_pipe<T>(nullptr, X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, plan->scan, nobs, ob_begin,
+                                               ob_end, y_begin, y_end, loc_mode, counters, st, plan);
+        cudaEventRecord(plan->used, st);
+        plan->was_used = true;
+        return rc;
+    }
     float4 *scan = nullptr;
     EXB_CUDA(exb_malloc_async(&scan, (size_t)nobs * sizeof(float4), st));
     su_scan_records_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, st>>>(obgeo, rec, nobs, scan);
@@ -422,6 +437,23 @@ static int state_sweep_impl(T *X, int64_t nlev, int64_t ny, int64_t nx, int nens
                                            ob_end, y_begin, y_end, loc_mode, counters, st);
     cudaFreeAsync(scan, st);
     return rc;
+}
+
+extern "C" int exb_state_sweep_planned_f64(void *plan, double *X, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                                           const double *grid_u, const double *Yp, const double *rec, const double *obgeo,
+                                           int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end,
+                                           int loc_mode, unsigned long long *counters, void *stream) {
+    EXB_REQUIRE(plan, "null plan");
+    return state_sweep_impl<double>(X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, nobs, ob_begin, ob_end, y_begin, y_end,
+                                    loc_mode, counters, stream, static_cast<ExbSweepPlan *>(plan));
+}
+extern "C" int exb_state_sweep_planned_f32(void *plan, float *X, int64_t nlev, int64_t ny, int64_t nx, int nens,
+                                           const double *grid_u, const float *Yp, const double *rec, const double *obgeo,
+                                           int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin, int64_t y_end,
+                                           int loc_mode, unsigned long long *counters, void *stream) {
+    EXB_REQUIRE(plan, "null plan");
+    return state_sweep_impl<float>(X, nlev, ny, nx, nens, grid_u, Yp, rec, obgeo, nobs, ob_begin, ob_end, y_begin, y_end,
+                                   loc_mode, counters, stream, static_cast<ExbSweepPlan *>(plan));
 }
 
 extern "C" int exb_state_sweep_f64(double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,

@@ -286,6 +286,29 @@ class ObsPlan:
             self.handle = C.c_void_p()
 
 
+class SweepPlan:
+    """The geometry-only part of the fused state sweep (scan records of the obs, candidate lists per coarse tile),
+    built on a side stream while the ob priors and the obs-space solve are computed (exb_sweep_plan_create)."""
+
+    def __init__(self, grid_u, nlev, ny, nx, obs_dev, geo, nobs, loc_mode, y_begin=0, y_end=None):
+        torch = _torch()
+        self.handle = C.c_void_p()
+        self.grid_u, self.geo = grid_u, geo          # keep the inputs alive and identical to what the sweep is given
+        self.stream = torch.cuda.Stream(device=geo.device)
+        ready = obs_dev.get('_ready')
+        if ready is not None:
+            self.stream.wait_event(ready)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        _lib.call('exb_sweep_plan_create', _lib.ptr(grid_u), nlev, ny, nx, _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs,
+                  0, nobs, y_begin, ny if y_end is None else y_end, loc_mode, C.c_void_p(self.stream.cuda_stream),
+                  C.byref(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            _lib.call('exb_sweep_plan_destroy', self.handle)
+            self.handle = C.c_void_p()
+
+
 _DIST_BUFFERS = {}
 
 
@@ -372,6 +395,11 @@ def obs_dist_block():
     return max(1, int(os.environ.get('EXB_OBS_DIST_BLOCK', '1')))
 
 
+def sweep_plan_wanted():
+    import os
+    return os.environ.get('EXB_SWEEP_PLAN', '1') != '0'
+
+
 def obs_plan_wanted(loc_mode):
     import os
     return loc_mode == LOC_GC and os.environ.get('EXB_OBS_IMPL', 'dag') == 'dag' and os.environ.get('EXB_OBS_PLAN', '1') != '0'
@@ -384,9 +412,14 @@ def state_update(xm, Xp, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, cou
 
 
 def state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, nobs, loc_mode, counters, y_begin=0, y_end=None,
-                      ob_begin=0, ob_end=None):
-    """Fused split + sweep + recombine of grid rows [y_begin, y_end) of a float64 shard holding full ensemble
-    values (exb_state_sweep_f64)."""
+                      ob_begin=0, ob_end=None, plan=None):
+    """Fused split + sweep + recombine of grid rows [y_begin, y_end) of a shard holding full ensemble values
+    (exb_state_sweep_f64 / _f32; with a SweepPlan the geometry-only part was built ahead)."""
+    if plan is not None:
+        _lib.call('exb_state_sweep_planned_' + _sfx(X.dtype), plan.handle, _lib.ptr(X), nlev, ny, nx, X.shape[-1],
+                  _lib.ptr(grid_u), _lib.ptr(Yp), _lib.ptr(rec), _lib.ptr(geo), nobs, ob_begin, nobs if ob_end is None else ob_end,
+                  y_begin, ny if y_end is None else y_end, loc_mode, _lib.ptr(counters), _lib.stream_ptr())
+        return
     _lib.call('exb_state_sweep_' + _sfx(X.dtype), _lib.ptr(X), nlev, ny, nx, X.shape[-1], _lib.ptr(grid_u), _lib.ptr(Yp),
               _lib.ptr(rec), _lib.ptr(geo), nobs, ob_begin, nobs if ob_end is None else ob_end, y_begin,
               ny if y_end is None else y_end, loc_mode, _lib.ptr(counters), _lib.stream_ptr())
@@ -479,6 +512,7 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
     tm = _Timer(timing)
     tm.mark('start')
     plan = None
+    splan = None
     with torch.cuda.device(dev):
         if inflation is not None:
             fac = np.ascontiguousarray(inflation, dtype=np.float64).ravel()
@@ -505,6 +539,11 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                                obs_dist_block())
             elif obs_plan_wanted(loc_mode):
                 plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
+            fused = fused_sweep_available(X.dtype, nens)
+            grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
+            if fused and sweep_plan_wanted():
+                # candidate lists of the sweep: geometry only as well, built on another side stream meanwhile
+                splan = SweepPlan(grid_u, nlev, ny, nx, obs_dev, geo, obs.nobs, loc_mode)
             if Y is None:
                 Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group, obs_dev=obs_dev)
             elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
@@ -513,7 +552,6 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
             Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
             _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
-            fused = fused_sweep_available(X.dtype, nens)
             if not fused:
                 xm = torch.empty(nrows, dtype=X.dtype, device=dev)
                 _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
@@ -535,12 +573,11 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             if not done:
                 obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
             tm.mark('obs_solve')
-            grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
             if fused:
                 for ya, yb in (sweep_bands or [(0, ny)]):
                     if before_band is not None:
                         before_band(ya, yb)
-                    state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb)
+                    state_sweep_fused(X, nlev, ny, nx, grid_u, Yp, rec, geo, obs.nobs, loc_mode, counters, ya, yb, plan=splan)
                     if on_band_done is not None:
                         on_band_done(ya, yb)
                 tm.mark('state_update')
@@ -556,6 +593,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         finally:
             if plan is not None:
                 plan.destroy()
+            if splan is not None:
+                splan.destroy()
     return AnalysisResult(prior_mean=rec_h[0], prior_var=rec_h[1], post_mean=rec_h[2], post_var=rec_h[3],
                           assimilated=rec_h[7] != 0.0, n_exact=nex_h, state_pairs=int(cnt[1]) * nlev,
                           obs_pairs=int(cnt[0]), ms=tm.result(), obs_solve=which)

@@ -247,6 +247,25 @@ int exb_state_sweep_f32(float *X, int64_t nlev, int64_t ny, int64_t nx, int nens
                         int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
                         void *stream);
 
+/* The part of exb_state_sweep_* that depends on the geometry only (fp32 scan records of the obs, candidate lists per
+ * coarse tile of the grid) can be built ahead -- on another stream, while the ob priors and the obs-space solve are
+ * computed: exb_sweep_plan_create enqueues it on ITS stream (synchronising that stream once, to size the lists) for grid
+ * rows [y_begin, y_end) and obs [ob_begin, ob_end); exb_state_sweep_planned_* makes its stream wait for the plan and
+ * sweeps any row sub-range of it; exb_sweep_plan_destroy frees it (in stream order after the last sweep that used it).
+ * ob_assimilate must be the flags the obs-space solve is given. */
+int exb_sweep_plan_create(const double *grid_u, int64_t nlev, int64_t ny, int64_t nx, const double *obgeo,
+                          const uint8_t *ob_assimilate, int64_t nobs, int64_t ob_begin, int64_t ob_end, int64_t y_begin,
+                          int64_t y_end, int loc_mode, void *stream, void **plan);
+int exb_sweep_plan_destroy(void *plan);
+int exb_state_sweep_planned_f64(void *plan, double *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                                const double *Yp, const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin,
+                                int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                                void *stream);
+int exb_state_sweep_planned_f32(void *plan, float *X, int64_t nlev, int64_t ny, int64_t nx, int nens, const double *grid_u,
+                                const float *Yp, const double *rec, const double *obgeo, int64_t nobs, int64_t ob_begin,
+                                int64_t ob_end, int64_t y_begin, int64_t y_end, int loc_mode, unsigned long long *counters,
+                                void *stream);
+
 /* Number of grid rows per patch row of exb_state_sweep_f64 for this shape (a small positive integer, not a status
  * code): row ranges whose edges are multiples of it are swept without splitting a patch between two calls. */
 int exb_state_sweep_row_granularity(int64_t nlev, int64_t ny, int64_t nx);

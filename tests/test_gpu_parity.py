@@ -391,6 +391,7 @@ def test_sweep_variants_agree(kw):
     ny = case.lat2d.shape[0]
     runs = {
         'pipe_fused': _analysis_with_env(case, {}),
+        'pipe_noplan': _analysis_with_env(case, {'EXB_SWEEP_PLAN': '0'}),
         'pipe_v3': _analysis_with_env(case, {'EXB_SP_IMPL': 'v3'}),
         'pipe_v3_split': _analysis_with_env(case, {'EXB_SP_IMPL': 'v3', 'EXB_FUSED': '0'}),
         'pipe_nolist': _analysis_with_env(case, {'EXB_SWEEP_NOLIST': '1'}),

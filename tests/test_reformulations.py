@@ -137,6 +137,10 @@ def test_fast_localisation_weight_constants_and_accuracy():
         pe, po = pe * a2 + exact[2 * k], po * a2 + exact[2 * k + 1]
     q = po * a + pe
     np.testing.assert_allclose(np.sqrt(a) * q, np.arcsin(np.sqrt(a)), rtol=4e-16)
+    # the same coefficients again in the parameter-block table of the lean weight function (exb_loc_const)
+    tab = src[src.index('const double c[20] = {'):]
+    tab = [float(x) for x in re.findall(r'[0-9.]+(?:e-?[0-9]+)?', tab[tab.index('{') + 1:tab.index('}')])]
+    assert tab == exact
     # the 10-term series of exb_asin_sqrt_over_sqrt_short: same coefficients c0..c9, valid up to EXB_SHORT_AMAX = 0.03
     sbody = src[src.index('double exb_asin_sqrt_over_sqrt_short'):src.index('template <bool SHORT>')]
     scoef = [float(x) for x in re.findall(r'fma\(p[eo], a2, ([0-9.e-]+)\)', sbody)] + \
