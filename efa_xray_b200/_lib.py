@@ -19,6 +19,7 @@ SIGNATURES = {
     'exb_version': [],
     'exb_device_check': [],
     'exb_grid_unitvec': [_p, _p, _i64, _p, _p],
+    'exb_obs_trig': [_p, _p, _i64, _p, _p, _p],
     'exb_obs_prepare': [_p, _p, _p, _i64, _int, _p, _p],
     'exb_stencil_search': [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     'exb_stencil_search_rect': [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p],

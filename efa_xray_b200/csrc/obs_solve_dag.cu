@@ -463,6 +463,11 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         r.mj = (double)__ldcg(a.Ym + j);
         r.dead = false;
         const double ux = a.geo[GEO_UX * nobs + j], uy = a.geo[GEO_UY * nobs + j], uz = a.geo[GEO_UZ * nobs + j];
+        // the ob's own scalars are fetched now: at the end of the row they would sit on the critical path of the
+        // dependency chain (the next ob of the chain is waiting for this record)
+        const double my_val = __ldg(a.ob_value + j), my_err = __ldg(a.ob_error + j);
+        const bool act = __ldg(a.ob_assim + j) != 0;
+        const double sq_err = sqrt(my_err);
         const int64_t oi = DIST ? (int64_t)t : j;       // lists are indexed by the rank's own row number when distributed
         const int64_t lb = a.off[oi] - a.list_base, le = a.off[oi + 1] - a.list_base;
 
@@ -497,26 +502,13 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         if (r.dead) break;
 
         // ---- this ob's own step: ensrf.py:61-91, :135, :144-149 ----
-        double s0 = 0.0, q0 = 0.0;
-#pragma unroll
-        for (int q = 0; q < MC; ++q) { const double v = (double)r.x[q]; s0 += v; q0 += v * v; }
-        const double rs = dg_warp_sum(s0), rq = dg_warp_sum(q0);
-        const double my_val = a.ob_value[j], my_err = a.ob_error[j];
-        const bool act = a.ob_assim[j] != 0;
-        const double mj = r.mj;
-        const double mean = rs * inv_n;
-        const double varye = fmax(rq * inv_n - mean * mean, 0.0);                    // np.var, ddof 0
-        const double innov = my_val - mj;
-        const double kdenom = varye + my_err;
-        const double c1 = 1.0 / ((double)(nens - 1) * kdenom);
-        const double beta = 1.0 / (1.0 + sqrt(my_err) * rsqrt(kdenom));              // 1/(1+sqrt(R/kdenom))
-
-        // publish (data first, the polled word last); skipped obs are never anyone's predecessor
-        if (act) {
+        // The ye row goes out first (data before the polled word): its stores travel while the scalars are computed.
+        // Skipped obs are never anyone's predecessor: their scalars stay unpublished; the distributed variant still
+        // publishes their ye row, so that every rank ends up with all ye rows in its own record buffer.
+        if (act || DIST) {
             unsigned long long pw[NW];
 #pragma unroll
             for (int c = 0; c < NW; ++c) pw[c] = DgWord<T>::pack(r.x + c * PER);
-            const unsigned long long s0 = dg_pack_scalar(c1 * innov), s1 = dg_pack_scalar(c1 * beta);
             if (!DIST) {
                 unsigned long long *p = reinterpret_cast<unsigned long long *>(a.P + (j * 32 + lane) * MC);
                 if (lane * MC < nens) {
@@ -528,7 +520,6 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
                         for (int c = 0; c < NW; c += 2) dg_st16(p + c, pw[c], pw[c + 1]);
                     }
                 }
-                if (lane == 0) dg_st16(a.S + j * 2, s0, s1);
             } else {
                 // own copy first (local readers are the closest in index), then the peers
                 for (int q = 0; q < a.world; ++q) {
@@ -544,11 +535,28 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
                         }
                     }
                 }
-                if (lane == 0)
-                    for (int q = 0; q < a.world; ++q) {
-                        const int dst = (a.rank + q) % a.world;
-                        dg_st16_sys(static_cast<double *>(a.S_peer[dst]) + j * 2, s0, s1);
-                    }
+            }
+        }
+        double s0 = 0.0, q0 = 0.0;
+#pragma unroll
+        for (int q = 0; q < MC; ++q) { const double v = (double)r.x[q]; s0 += v; q0 += v * v; }
+        const double rs = dg_warp_sum(s0), rq = dg_warp_sum(q0);
+        const double mj = r.mj;
+        const double mean = rs * inv_n;
+        const double varye = fmax(rq * inv_n - mean * mean, 0.0);                    // np.var, ddof 0
+        const double innov = my_val - mj;
+        const double kdenom = varye + my_err;
+        const double c1 = 1.0 / ((double)(nens - 1) * kdenom);
+        const double beta = 1.0 / (1.0 + sq_err * rsqrt(kdenom));                    // 1/(1+sqrt(R/kdenom))
+        if (act && lane == 0) {
+            const unsigned long long s0w = dg_pack_scalar(c1 * innov), s1w = dg_pack_scalar(c1 * beta);
+            if (!DIST) {
+                dg_st16(a.S + j * 2, s0w, s1w);
+            } else {
+                for (int q = 0; q < a.world; ++q) {
+                    const int dst = (a.rank + q) % a.world;
+                    dg_st16_sys(static_cast<double *>(a.S_peer[dst]) + j * 2, s0w, s1w);
+                }
             }
         }
         // outputs of the C ABI: ye_j / mye_j in place, per-ob records

@@ -51,6 +51,24 @@ __global__ void obs_prepare_kernel(const double *__restrict__ lat, const double 
     geo[GEO_THETA * nobs + i] = theta;
 }
 
+// sin(radians(lat)), cos(radians(lon)) of the obs: the ob-side tables of the nearest-point search
+// (state/ensemble.py:160-163), same operations as numpy's: x * (pi / 180), then sin / cos
+__global__ void obs_trig_kernel(const double *__restrict__ lat, const double *__restrict__ lon, int64_t nobs,
+                                double *__restrict__ sinlat, double *__restrict__ coslon) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nobs) return;
+    sinlat[i] = sin(lat[i] * EXB_DEG2RAD);
+    coslon[i] = cos(lon[i] * EXB_DEG2RAD);
+}
+
+extern "C" int exb_obs_trig(const double *ob_lat_deg, const double *ob_lon_deg, int64_t nobs, double *ob_sinlat,
+                            double *ob_coslon, void *stream) {
+    EXB_REQUIRE(ob_lat_deg && ob_lon_deg && ob_sinlat && ob_coslon && nobs > 0, "null pointer or nobs <= 0");
+    obs_trig_kernel<<<(unsigned)ceil_div64(nobs, 256), 256, 0, (cudaStream_t)stream>>>(ob_lat_deg, ob_lon_deg, nobs, ob_sinlat, ob_coslon);
+    exb_count_launches(1);
+    return exb_check_launch("obs_trig_kernel");
+}
+
 // ------------------------------------------------------------------------------------------
 // nearest-4 search under the reference's pseudo-metric (state/ensemble.py:160-165)
 // ------------------------------------------------------------------------------------------

@@ -59,6 +59,8 @@ struct S2Params {
     double *scratch;                  // per CTA: S2_CAND/8 blocks of blk_doubles, then the parked rows
     const int *abort_flag;            // watchdog word of the obs-space solve that produced the records (may be null)
     unsigned long long *prof;         // EXB_S2_PROF=1: clocks of warp 0 per phase, summed over CTAs (null: off)
+    int dbg;                          // EXB_S2_DEBUG bit mask, timing experiments only (2 and 4: results are wrong): 1 ye rows of the Gram matrix staged with cp.async,
+                                      // 2 no weights, 4 no Gram
     int64_t npts, nobs, ob_begin, ob_end, scratch_stride;
     int nlev, ny, nx, nens;
     int y_begin, y_end;               // grid rows [y_begin, y_end) of the shard are swept by this launch
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
     double *s_ring = reinterpret_cast<double *>(smem_raw);                                   // [nstages][stage_doubles]
     double *s_gu = s_ring + (size_t)p.nstages * p.stage_doubles;                             // [3][S2_ROWS]
     double *s_sob = s_gu + 3 * S2_ROWS;                                                      // [S2_NW][8][6]
-    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_sob + S2_NW * 48); // [S2_MAXSTAGES]
+    double2 *s_xch = reinterpret_cast<double2 *>(s_sob + S2_NW * 48);                          // [S2_NW][32]
+    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_xch + S2_NW * 32); // [S2_MAXSTAGES]
     unsigned long long *s_empty = s_full + S2_MAXSTAGES;                                      // [S2_MAXSTAGES]
     int *s_cand = reinterpret_cast<int *>(s_empty + S2_MAXSTAGES);                            // [S2_CAND]
     int *s_gvalid = s_cand + S2_CAND;                                                         // [S2_ROWS]
@@ -335,7 +338,9 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 // the ring is idle in this phase: every warp stages the 8 ye rows of its current batch in it (cp.async)
                 // while it evaluates the weights, and forms the Gram matrix from there afterwards
                 double *stg = s_ring + (size_t)warp * (8 * YW);
-                const bool stage_rows = (size_t)S2_NW * 8 * YW <= (size_t)S * SD;
+                // (measured: staging costs 1.7 % of the kernel more than loading the operands straight from L2 after the
+                // weights, EXB_S2_DEBUG=1 switches it on)
+                const bool stage_rows = (size_t)S2_NW * 8 * YW <= (size_t)S * SD && (p.dbg & 1);
                 // scalars of the obs of a batch, held by lanes 0..7; loaded one batch ahead
                 struct ObSc { double ux, uy, uz, ihw, amax, c1, beta; int kk; };      // (no arithmetic on the loaded values
                                                                                      // here: it would wait for them)
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                         npb += (w != 0.0) ? 1 : 0;
                         return w * o45.y;
                     };
-                    const int nfull = G >> 5, R = G & 31;
+                    const int nfull = (p.dbg & 2) ? 0 : (G >> 5), R = (p.dbg & 2) ? 0 : (G & 31);
                     for (int sl = 0; sl < nfull; ++sl) {
                         const int gg = lane + 32 * sl;
                         const double gx = s_gu[gg], gy = s_gu[S2_ROWS + gg], gz = s_gu[2 * S2_ROWS + gg];
@@ -430,7 +435,8 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     // this lane's two members of every 8-member tile
                     {
                         double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
-                        if (stage_rows) {
+                        if (p.dbg & 4) {
+                        } else if (stage_rows) {
                             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
                             __syncwarp();
                             const double *yrow = stg + n * YW + 2 * c;
@@ -567,12 +573,17 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                                 s2_dmma(ga0, ga1, a1, v.y);
                             }
                         }
-                        // lane c of a row holds g[row][2c], g[row][2c+1]: obs 0..3 are broadcast to the row's 4 lanes now,
-                        // obs 4..7 after their correction by obs 0..3 below
+                        // lane c of a row holds g[row][2c], g[row][2c+1]: the row's 4 lanes exchange them through shared
+                        // memory (1 store + 2 loads of 16 bytes instead of 8 shuffles; measured 2 % of the loop): obs 0..3
+                        // now, obs 4..7 after their correction by obs 0..3 below
                         double gq[8];
-                        const int l0r = lane & ~3;
-                        gq[0] = __shfl_sync(0xffffffffu, ga0, l0r); gq[1] = __shfl_sync(0xffffffffu, ga1, l0r);
-                        gq[2] = __shfl_sync(0xffffffffu, ga0, l0r + 1); gq[3] = __shfl_sync(0xffffffffu, ga1, l0r + 1);
+                        double2 *xg = s_xch + warp * 32 + (lane & ~3);
+                        xg[c] = make_double2(ga0, ga1);
+                        __syncwarp();
+                        {
+                            const double2 t0 = xg[0], t1 = xg[1];
+                            gq[0] = t0.x; gq[1] = t0.y; gq[2] = t1.x; gq[3] = t1.y;
+                        }
                         // step 2: the serial recurrence inside the batch (per row; every lane of the row computes it)
                         double e[8];
                         e[0] = om[0] * gq[0];
@@ -586,8 +597,11 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                             // B[k][j] = G[j][k] for the columns j = 4..7
                             double k0 = ga0, k1 = ga1;
                             s2_dmma(k0, k1, ea, (n >= 4) ? Gb[n * 8 + c] : 0.0);
-                            gq[4] = __shfl_sync(0xffffffffu, k0, l0r + 2); gq[5] = __shfl_sync(0xffffffffu, k1, l0r + 2);
-                            gq[6] = __shfl_sync(0xffffffffu, k0, l0r + 3); gq[7] = __shfl_sync(0xffffffffu, k1, l0r + 3);
+                            __syncwarp();                           // everybody has read obs 0..3
+                            xg[c] = make_double2(k0, k1);
+                            __syncwarp();
+                            const double2 t2 = xg[2], t3 = xg[3];
+                            gq[4] = t2.x; gq[5] = t2.y; gq[6] = t3.x; gq[7] = t3.y;
                         }
                         e[4] = om[4] * gq[4];
                         e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
@@ -703,7 +717,7 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     EXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t fixed = sizeof(double) * (3 * S2_ROWS + S2_NW * 48) + sizeof(unsigned long long) * 2 * S2_MAXSTAGES +
+    const size_t fixed = sizeof(double) * (3 * S2_ROWS + S2_NW * 48 + S2_NW * 64) + sizeof(unsigned long long) * 2 * S2_MAXSTAGES +
                          sizeof(int) * (S2_CAND + S2_ROWS + S2_NW + 4) + sizeof(float) * 4 + 128;
     int S = (int)(((size_t)max_smem - 1024 - fixed) / (sizeof(double) * p.stage_doubles));
     if (S > S2_MAXSTAGES) S = S2_MAXSTAGES;
@@ -764,6 +778,7 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
             else prof = nullptr;
         }
         p.prof = prof;
+        p.dbg = getenv("EXB_S2_DEBUG") ? atoi(getenv("EXB_S2_DEBUG")) : 0;
         state_sweep_2p_kernel<NT3, TS><<<(unsigned)grid, S2_NT, smem, st>>>(p);
         exb_count_launches(2);
         rc = exb_check_launch("state_sweep_2p_kernel");

@@ -367,16 +367,20 @@ def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, s
     if rc != 0:
         raise _lib.ExbError('exb_obs_solve_dist_%s failed (%d): %s' % (sfx, rc, lib.exb_last_error().decode('utf-8', 'replace')))
     mine = (torch.arange(nobs, device=Yp.device) // plan.block) % world == rank
-    Yp.mul_(mine[:, None].to(Yp.dtype))
     Ym.mul_(mine.to(Ym.dtype))
     # NaN marks "not assimilated" in the records (post mean / variance): keep it out of the sum
     nanmask = torch.isnan(rec)
     rec.masked_fill_(nanmask, 0.0)
     skipped = nanmask.to(rec.dtype)
-    for t in (Yp, Ym, rec, skipped, counters[0:1]):
+    for t in (Ym, rec, skipped, counters[0:1]):
         dist.all_reduce(t, group=g)
     rec.masked_fill_(skipped > 0, float('nan'))
     counters[0:1].add_(c0)
+    # every rank's record buffer holds the published ye row of EVERY ob once all ranks are done (the all-reduces above
+    # are behind every rank's kernel): the 80 MB of ye rows need no collective, only a local copy out of the padded
+    # records
+    mc = P.numel() // (nobs * 32)
+    Yp.copy_(P.view(nobs, 32 * mc)[:, :nens])
     return True
 
 
@@ -390,9 +394,11 @@ def obs_dist_wanted(group):
 
 
 def obs_dist_block():
-    """Block size of the distributed obs-space solve's dealing (EXB_OBS_DIST_BLOCK, default 1 = round-robin)."""
+    """Block size of the distributed obs-space solve's dealing (EXB_OBS_DIST_BLOCK; 1 = round-robin).  Default 256:
+    consecutive obs of a dependency chain are a few tens of indices apart, so most hops of the chain then stay on one
+    GPU (measured at N = 2, config 3: 17.5 ms against 22.8 ms round-robin and 20.2 ms replicated)."""
     import os
-    return max(1, int(os.environ.get('EXB_OBS_DIST_BLOCK', '1')))
+    return max(1, int(os.environ.get('EXB_OBS_DIST_BLOCK', '256')))
 
 
 def sweep_plan_wanted():
@@ -435,13 +441,13 @@ def fused_sweep_available(dtype, nens):
     return os.environ.get('EXB_SU_IMPL', 'pipe') == 'pipe'
 
 
-_OBS_FIELDS = ('value', 'error', 'lat', 'lon', 'halfwidth', 'sinlat', 'coslon', 'tw0', 'tw1', 'row0', 'row1')
+_OBS_FIELDS = ('value', 'error', 'lat', 'lon', 'halfwidth', 'tw0', 'tw1', 'row0', 'row1')
 _STAGING = {}
 
 
 def upload_obs(obs: ObsArrays, device, loc_mode):
     """Per-ob tables on the device + the obgeo block of exb_obs_prepare.  Everything goes up in ONE copy from a cached
-    page-locked staging buffer (eleven 8-byte fields + the assimilate flags per ob): small pageable copies cost a
+    page-locked staging buffer (nine 8-byte fields + the assimilate flags per ob): small pageable copies cost a
     host synchronisation each and may not queue behind bulk state copies."""
     torch = _torch()
     n = obs.nobs
@@ -460,10 +466,8 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
     i64 = hb[:nf * n * 8].view(np.int64).reshape(nf, n)
     f64[0], f64[1], f64[2], f64[3] = obs.value, obs.error, obs.lat, obs.lon
     f64[4] = obs.halfwidth if loc_mode == LOC_GC else 1.0
-    np.sin(np.radians(f64[2]), out=f64[5])
-    np.cos(np.radians(f64[3]), out=f64[6])
-    f64[7], f64[8] = obs.tw0, obs.tw1
-    i64[9], i64[10] = obs.row0, obs.row1
+    f64[5], f64[6] = obs.tw0, obs.tw1
+    i64[7], i64[8] = obs.row0, obs.row1
     hb[nf * n * 8:] = obs.assimilate
     db = torch.empty(nf * n * 8 + n, dtype=torch.uint8, device=device)
     db.copy_(ent['host'], non_blocking=True)
@@ -476,6 +480,10 @@ def upload_obs(obs: ObsArrays, device, loc_mode):
     d['_buffer'] = db
     if loc_mode != LOC_GC:
         d['halfwidth'] = None
+    # ob-side tables of the nearest-point search, on the device (5 ms of host trigonometry for 1e5 obs otherwise)
+    trig = torch.empty((2, n), dtype=torch.float64, device=device)
+    _lib.call('exb_obs_trig', _lib.ptr(d['lat']), _lib.ptr(d['lon']), n, _lib.ptr(trig[0]), _lib.ptr(trig[1]), _lib.stream_ptr())
+    d['sinlat'], d['coslon'] = trig[0], trig[1]
     geo = torch.empty((8, n), dtype=torch.float64, device=device)
     _lib.call('exb_obs_prepare', _lib.ptr(d['lat']), _lib.ptr(d['lon']), _lib.ptr(d['halfwidth']), n,
               loc_mode, _lib.ptr(geo), _lib.stream_ptr())
@@ -529,6 +537,7 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
         # (small host-to-device copies: callers that stream the state in on another stream do them first and pass
         # the result, or they would queue behind the state in the copy engine)
         obs_dev, geo = obs_device if obs_device is not None else upload_obs(obs, dev, loc_mode)
+        tm.mark('setup_upload')
         try:
             # predecessor lists of the obs-space solve: geometry only, started on a side stream now so that they are
             # built while the host and this stream work on the ob priors
@@ -541,9 +550,6 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
             fused = fused_sweep_available(X.dtype, nens)
             grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
-            if fused and sweep_plan_wanted():
-                # candidate lists of the sweep: geometry only as well, built on another side stream meanwhile
-                splan = SweepPlan(grid_u, nlev, ny, nx, obs_dev, geo, obs.nobs, loc_mode)
             if Y is None:
                 Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group, obs_dev=obs_dev)
             elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
@@ -552,12 +558,18 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 Yp, nex = Y.clone(), torch.zeros(1, dtype=torch.int32, device=dev)
             Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
             _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
+            tm.mark('setup_ob_priors')
+            if fused and sweep_plan_wanted():
+                # candidate lists of the sweep: geometry only as well, built on another side stream.  Creating the plan
+                # blocks the host until its counting pass is done, so it comes after the ob priors have been enqueued
+                # (the device computes them meanwhile)
+                splan = SweepPlan(grid_u, nlev, ny, nx, obs_dev, geo, obs.nobs, loc_mode)
             if not fused:
                 xm = torch.empty(nrows, dtype=X.dtype, device=dev)
                 _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
             if plan is not None:
                 plan.finish()
-            tm.mark('setup')
+            tm.mark('setup_plans')
             rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
             counters = torch.zeros(2, dtype=torch.int64, device=dev)
             done = False

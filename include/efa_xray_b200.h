@@ -68,6 +68,11 @@ int exb_grid_unitvec(const double *lat_deg, const double *lon_deg, int64_t npts,
 int exb_obs_prepare(const double *ob_lat_deg, const double *ob_lon_deg, const double *ob_halfwidth_km,
                     int64_t nobs, int loc_mode, double *obgeo, void *stream);
 
+/* sin(radians(lat)) and cos(radians(lon)) of the obs: the ob-side tables exb_stencil_search* take.  (An exact tie
+ * between two grid points of the pseudo-metric is a symmetry of the GRID tables and does not depend on these.) */
+int exb_obs_trig(const double *ob_lat_deg, const double *ob_lon_deg, int64_t nobs, double *ob_sinlat, double *ob_coslon,
+                 void *stream);
+
 /* Distances (km) and localisation weights from ONE observation to n points given as unit vectors
  * (SoA double[3][n], from exb_grid_unitvec): Observation.distance_to_state / Observation.localize for a
  * state or a list of obs (observation/observation.py:53-87).  Either output may be NULL. */

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out; mkdir -p $O
+echo "== quick tests"; timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sweep_variants or golden or obs_solve or edge or config1 or forward or one_dim" > $O/r02m_quick.log 2>&1; echo "quick rc=$?"; tail -4 $O/r02m_quick.log
+echo "== bench"; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-api > $O/r02m_bench.json 2> $O/r02m_bench.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r02m_bench.json') if l.startswith('{')][-1])
+print('ms', round(d['ms_per_step'],2), 'phases', {k:round(v,2) for k,v in d['phases_ms'].items()}, 'fp64 frac', round(d['roofline_fp64']['frac'],3))
+PY
+echo "== prof"; EXB_S2_PROF=1 timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-api 2>&1 | grep "s2 prof" | tail -1

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(TILES == 2 ? 256 : NTHR, 1) k(double *out, lon
     __shared__ __align__(16) double sy[8 * YST + 16];
     __shared__ __align__(16) double som[48 * 8];
     __shared__ double Gb[64];
+    __shared__ __align__(16) double xch[16 * 32 * 2];
     for (int i = threadIdx.x; i < 8 * YST + 16; i += blockDim.x) sy[i] = 1e-3 * ((i * 7) % 13) - 5e-3;
     for (int i = threadIdx.x; i < 48 * 8; i += blockDim.x) som[i] = 1e-4 * (1 + i % 5);
     for (int i = threadIdx.x; i < 64; i += blockDim.x) Gb[i] = 1e-2 * (1 + i % 3);
@@ -75,6 +76,29 @@ __global__ void __launch_bounds__(TILES == 2 ? 256 : NTHR, 1) k(double *out, lon
                 const double o0 = __shfl_xor_sync(0xffffffffu, k0, 1), o1 = __shfl_xor_sync(0xffffffffu, k1, 1);
                 if (c & 1) { gq[4] -= o0; gq[5] -= o1; gq[6] -= k0; gq[7] -= k1; }
                 else { gq[4] -= k0; gq[5] -= k1; gq[6] -= o0; gq[7] -= o1; }
+                e[4] = om[4] * gq[4];
+                e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
+                e[6] = om[6] * (gq[6] - Gb[52] * e[4] - Gb[53] * e[5]);
+                e[7] = om[7] * (gq[7] - Gb[60] * e[4] - Gb[61] * e[5] - Gb[62] * e[6]);
+            } else if (REC == 4) {
+                // all-gather through shared memory: every lane stores its two dots, the row's lanes read four back
+                double2 *xg = reinterpret_cast<double2 *>(xch) + (warp * 32 + (lane & ~3));
+                xg[c] = make_double2(ga0, ga1);
+                __syncwarp();
+                const double2 t0 = xg[0], t1 = xg[1];
+                gq[0] = t0.x; gq[1] = t0.y; gq[2] = t1.x; gq[3] = t1.y;
+                e[0] = om[0] * gq[0];
+                e[1] = om[1] * (gq[1] - Gb[8] * e[0]);
+                e[2] = om[2] * (gq[2] - Gb[16] * e[0] - Gb[17] * e[1]);
+                e[3] = om[3] * (gq[3] - Gb[24] * e[0] - Gb[25] * e[1] - Gb[26] * e[2]);
+                const double ea = -((c == 0) ? e[0] : (c == 1) ? e[1] : (c == 2) ? e[2] : e[3]);
+                double k0 = ga0, k1 = ga1;
+                dmma(k0, k1, ea, (n >= 4) ? Gb[n * 8 + c] : 0.0);
+                __syncwarp();
+                xg[c] = make_double2(k0, k1);
+                __syncwarp();
+                const double2 t2 = xg[2], t3 = xg[3];
+                gq[4] = t2.x; gq[5] = t2.y; gq[6] = t3.x; gq[7] = t3.y;
                 e[4] = om[4] * gq[4];
                 e[5] = om[5] * (gq[5] - Gb[44] * e[4]);
                 e[6] = om[6] * (gq[6] - Gb[52] * e[4] - Gb[53] * e[5]);
@@ -149,7 +173,7 @@ void run(int warps) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     const double per_batch = (double)h / iters;               // clocks per loop iteration of one warp
-    const double dm = (52.0 + ((REC == 1 || REC == 3) ? 1 : 0)) * TILES;   // DMMAs per iteration per warp
+    const double dm = (52.0 + ((REC == 1 || REC == 3 || REC == 4) ? 1 : 0)) * TILES;   // DMMAs per iteration per warp
     const double util = dm * 16.0 * (warps / 4.0) / per_batch;
     const double tf = dm * 512.0 * warps * 148.0 * iters / (ms * 1e-3) / 1e12;
     printf("warps %2d tiles %d REC %d GATHER %d LDS %d NTHR %d CH %d : %6.0f clk per warp-iteration, DMMA pipe %5.1f%% of 1/16clk/SMSP, %.1f TFLOP/s (rows/SM %3d -> %5.1f clk per row-batch)\n",
@@ -158,12 +182,8 @@ void run(int warps) {
 }
 int main() {
     cudaError_t e = cudaGetLastError();
-    for (int w : {12, 16}) run<1, 1, 1, 1>(w);
-    for (int w : {16, 17}) run<1, 1, 1, 1, 544>(w);          // 120 registers per thread (17 warps per CTA)
-    for (int w : {12, 16}) run<1, 1, 1, 1, 512, 1>(w);       // single accumulator chain in step 1
-    for (int w : {12, 16}) run<3, 1, 1, 1>(w);               // cross-block correction in the DMMA accumulator
     for (int w : {12, 16}) run<3, 1, 1, 1, 512, 1>(w);
-    for (int w : {16, 17}) run<3, 1, 1, 1, 544, 1>(w);
+    for (int w : {12, 16}) run<4, 0, 1, 1, 512, 1>(w);       // all-gather through shared memory
     e = cudaDeviceSynchronize();
     printf("status %s\n", cudaGetErrorString(e));
     return 0;
