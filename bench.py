@@ -463,7 +463,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (state sweep) -----------------------------------------
     hbm_peak, peak_src = peaks()
     su_s = float(su_max.item()) * 1e-3
-    sweep_kernel = 'state_sweep_pipe_kernel' if (args.dtype == 'f64' and nens <= 103) else 'state_update_kernel'
+    sweep_kernel = ('state_sweep_2p_kernel' if os.environ.get('EXB_SP_IMPL') != 'v3' else 'state_sweep_pipe_kernel') \
+        if nens <= 103 else 'state_update_kernel'
     alg_bytes = state_pairs * 2.0 * (nens + 1) * esize          # |F_s| * 2 * (Nens+1) * sizeof(T)
     achieved = alg_bytes / su_s / 1e9 / world                   # per GPU
     flops = state_pairs * (4.0 * nens + 3.0)

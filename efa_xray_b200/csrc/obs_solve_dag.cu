@@ -463,11 +463,6 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         r.mj = (double)__ldcg(a.Ym + j);
         r.dead = false;
         const double ux = a.geo[GEO_UX * nobs + j], uy = a.geo[GEO_UY * nobs + j], uz = a.geo[GEO_UZ * nobs + j];
-        // the ob's own scalars are fetched now: at the end of the row they would sit on the critical path of the
-        // dependency chain (the next ob of the chain is waiting for this record)
-        const double my_val = __ldg(a.ob_value + j), my_err = __ldg(a.ob_error + j);
-        const bool act = __ldg(a.ob_assim + j) != 0;
-        const double sq_err = sqrt(my_err);
         const int64_t oi = DIST ? (int64_t)t : j;       // lists are indexed by the rank's own row number when distributed
         const int64_t lb = a.off[oi] - a.list_base, le = a.off[oi + 1] - a.list_base;
 
@@ -502,6 +497,11 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
         if (r.dead) break;
 
         // ---- this ob's own step: ensrf.py:61-91, :135, :144-149 ----
+        // (its own value / error / flag are loaded here and not at the start of the row: carried through the
+        // predecessor loop they cost registers the loop does not have -- measured 18.7 against 17.6 ms)
+        const double my_val = a.ob_value[j], my_err = a.ob_error[j];
+        const bool act = a.ob_assim[j] != 0;
+        const double sq_err = sqrt(my_err);
         // The ye row goes out first (data before the polled word): its stores travel while the scalars are computed.
         // Skipped obs are never anyone's predecessor: their scalars stay unpublished; the distributed variant still
         // publishes their ye row, so that every rank ends up with all ye rows in its own record buffer.

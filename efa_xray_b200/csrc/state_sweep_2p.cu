@@ -69,6 +69,7 @@ struct S2Params {
     int G, Lc, nlc;
     int loc_mode;
     int nstages, stage_doubles, blk_doubles, npatches;
+    int cand_cap;                     // candidates per chunk (<= S2_CAND): bounds the part of the scratch area in use
     ExbLocConst kloc;                 // constants of the localisation weight (parameter block = constant bank)
 };
 
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
         for (;;) {
             // =============================== PHASE A (1): candidates of this chunk ===============================
             int ncand = 0;
-            while (pos < le && ncand + S2_SCAN <= S2_CAND) {
+            while (pos < le && ncand + S2_SCAN <= p.cand_cap) {
                 const int64_t e0 = pos + 2 * tid;
                 int i0 = -1, i1 = -1;
                 if (e0 < le) i0 = list ? __ldg(list + e0) : (int)e0;
@@ -779,6 +780,8 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
         }
         p.prof = prof;
         p.dbg = getenv("EXB_S2_DEBUG") ? atoi(getenv("EXB_S2_DEBUG")) : 0;
+        p.cand_cap = S2_CAND;
+        if (const char *e = getenv("EXB_S2_CAP")) { const int v = atoi(e); if (v >= S2_SCAN && v <= S2_CAND) p.cand_cap = v; }
         state_sweep_2p_kernel<NT3, TS><<<(unsigned)grid, S2_NT, smem, st>>>(p);
         exb_count_launches(2);
         rc = exb_check_launch("state_sweep_2p_kernel");
