@@ -210,6 +210,7 @@ struct DgArgs {
     int *ticket;
     int *status;                 // != 0: watchdog fired (value = 1 + index of the record that never arrived)
     unsigned long long watchdog_ns;
+    int hot_poll;                // poll the record itself while waiting for the last predecessor of a batch (EXB_DAG_HOT)
     int64_t nobs, row_begin, row_end;
     int nens, loc_mode;
     // distributed variant (DIST): the rows dg_row(deal, t) are solved here; records are published into the P / S
@@ -403,9 +404,33 @@ __device__ __forceinline__ bool dg_step(const DgArgs<T> &a, int lane, DgRow<T, M
                                         DgRec<DgCfg<T, MC>::NW> &nxt) {
     constexpr int NW = DgCfg<T, MC>::NW;
     constexpr int PER = DgWord<T>::PER;
-    while (!dg_ready<T, MC>(cur)) {
-        if (!dg_wait(a.S, a.status, a.watchdog_ns, r.k, lane)) { r.dead = true; return false; }
-        dg_fetch<T, MC>(a, r.k, lane, cur);
+    if (!dg_ready<T, MC>(cur)) {
+        if (r.m == 0 && a.hot_poll) {
+            // The last entry of a batch of 32 predecessors is where a row sits while it is the next link of the
+            // dependency chain: poll the record itself, without back-off, so that the hop does not pay a sleep interval
+            // plus a second round trip to L2 after the wake-up.  (Few warps are in this state at a time.)
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            do {
+                __nanosleep(20);
+                dg_fetch<T, MC>(a, r.k, lane, cur);
+                if ((++spins & 8191u) == 0) {
+                    if (*reinterpret_cast<volatile int *>(a.status) != 0) { r.dead = true; return false; }
+                    const unsigned long long now = dg_globaltimer();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > a.watchdog_ns) {
+                        if (lane == 0) atomicCAS(a.status, 0, r.k + 1);
+                        r.dead = true;
+                        return false;
+                    }
+                }
+            } while (!dg_ready<T, MC>(cur));
+        } else {
+            do {
+                if (!dg_wait(a.S, a.status, a.watchdog_ns, r.k, lane)) { r.dead = true; return false; }
+                dg_fetch<T, MC>(a, r.k, lane, cur);
+            } while (!dg_ready<T, MC>(cur));
+        }
     }
     const bool more = r.m != 0;
     const double w = r.w;
@@ -593,6 +618,11 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+static int dg_hot_poll() {
+    const char *e = getenv("EXB_DAG_HOT");
+    return e ? atoi(e) : 1;
+}
+
 static unsigned long long dg_watchdog_ns(int64_t nobs) {
     double sec = DG_WATCHDOG_S + 1e-4 * (double)nobs;
     if (const char *e = getenv("EXB_WATCHDOG_S")) { const double v = atof(e); if (v > 0.0) sec = v; }
@@ -817,6 +847,7 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
         EXB_CUDA(cudaMemsetAsync(sd, 0, sizeof(int), st));      // stream-ordered: an earlier solve's verdict is its own
         a.status = sd;
         a.watchdog_ns = dg_watchdog_ns(nobs);
+        a.hot_poll = dg_hot_poll();
     }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
@@ -866,6 +897,7 @@ static int dg_solve_dist(void *plan, T *Ym, T *Yp, const double *ob_value, const
         EXB_CUDA(cudaMemsetAsync(sd, 0, sizeof(int), st));      // stream-ordered: an earlier solve's verdict is its own
         a.status = sd;
         a.watchdog_ns = dg_watchdog_ns(nobs);
+        a.hot_poll = dg_hot_poll();
     }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;

@@ -366,15 +366,7 @@ def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, s
         return False
     if rc != 0:
         raise _lib.ExbError('exb_obs_solve_dist_%s failed (%d): %s' % (sfx, rc, lib.exb_last_error().decode('utf-8', 'replace')))
-    mine = (torch.arange(nobs, device=Yp.device) // plan.block) % world == rank
-    Ym.mul_(mine.to(Ym.dtype))
-    # NaN marks "not assimilated" in the records (post mean / variance): keep it out of the sum
-    nanmask = torch.isnan(rec)
-    rec.masked_fill_(nanmask, 0.0)
-    skipped = nanmask.to(rec.dtype)
-    for t in (Ym, rec, skipped, counters[0:1]):
-        dist.all_reduce(t, group=g)
-    rec.masked_fill_(skipped > 0, float('nan'))
+    merge_distributed_records(Ym, rec, counters[0:1], plan.block, rank, world, g)
     counters[0:1].add_(c0)
     # every rank's record buffer holds the published ye row of EVERY ob once all ranks are done (the all-reduces above
     # are behind every rank's kernel): the 80 MB of ye rows need no collective, only a local copy out of the padded
@@ -382,6 +374,25 @@ def obs_solve_distributed(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, s
     mc = P.numel() // (nobs * 32)
     Yp.copy_(P.view(nobs, 32 * mc)[:, :nens])
     return True
+
+
+def merge_distributed_records(Ym, rec, pair_counter, block, rank, world, group):
+    """After a distributed obs-space solve every rank holds means / records / pair count of ITS rows only (rank r owns
+    ob j when (j // block) % world == r): zero the others and sum over the group, so that every rank ends up with the
+    complete, identical result.  NaN marks "not assimilated" in the records (post mean / variance) and must survive the
+    sum.  Pure torch (works on any backend; tests/test_sharding_gloo.py runs it over gloo)."""
+    torch = _torch()
+    import torch.distributed as dist
+    nobs = Ym.shape[0]
+    mine = (torch.arange(nobs, device=Ym.device) // block) % world == rank
+    Ym.mul_(mine.to(Ym.dtype))
+    rec.mul_(mine.to(rec.dtype)[None, :])           # (NaN * 0 = NaN: rows of other ranks are zero-filled by the caller)
+    nanmask = torch.isnan(rec)
+    rec.masked_fill_(nanmask, 0.0)
+    skipped = (nanmask & mine[None, :]).to(rec.dtype)
+    for t in (Ym, rec, skipped, pair_counter):
+        dist.all_reduce(t, group=group)
+    rec.masked_fill_(skipped > 0, float('nan'))
 
 
 def obs_dist_wanted(group):

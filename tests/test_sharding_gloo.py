@@ -134,3 +134,48 @@ def test_localize_stencil_numpy_and_torch_agree():
     for a, b in ((0, 3), (3, 9), (9, 11)):
         tot += sharding.localize_stencil(idx, w, nlev, ny, nx, a, b)[1]
     assert np.array_equal(tot, w)
+
+
+def _merge_worker(rank, world, port, q):
+    try:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        from efa_xray_b200.engine import merge_distributed_records
+        nobs, block = 37, 5
+        rng = np.random.default_rng(3)                      # same on every rank: the complete result
+        full_rec = rng.standard_normal((8, nobs))
+        skipped = rng.uniform(size=nobs) < 0.2
+        full_rec[2:4, skipped] = np.nan                      # post mean / variance of obs that were not assimilated
+        full_ym = rng.standard_normal(nobs)
+        pairs = rng.integers(1, 50, nobs)
+        mine = (np.arange(nobs) // block) % world == rank
+        # what a rank holds after exb_obs_solve_dist_*: its own rows, zeros elsewhere in rec, untouched input elsewhere in Ym
+        rec = torch.from_numpy(np.where(mine[None, :], full_rec, 0.0))
+        ym = torch.from_numpy(np.where(mine, full_ym, 123.0))
+        cnt = torch.tensor([int(pairs[mine].sum())])
+        merge_distributed_records(ym, rec, cnt, block, rank, world, None)
+        np.testing.assert_array_equal(ym.numpy(), full_ym)
+        np.testing.assert_array_equal(rec.numpy(), full_rec)          # NaNs where they were, bit-equal elsewhere
+        assert int(cnt.item()) == int(pairs.sum())
+        dist.destroy_process_group()
+        q.put((rank, 'ok'))
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, 'FAIL: ' + traceback.format_exc()))
+
+
+def test_distributed_solve_record_merge_over_gloo():
+    """engine.merge_distributed_records: every rank contributes the rows dealt to it (blocks of consecutive obs), the
+    sums rebuild the complete records on every rank, NaN (not assimilated) survives."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] == 'ok' for r in results), results
