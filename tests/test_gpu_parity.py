@@ -831,3 +831,20 @@ def test_one_dimensional_latlon_state_matches_reference_golden():
     near9 = state.nearest_points(obs[0].lat, obs[0].lon, npt=9)
     assert len(near9) == 1 and near9[0].shape == (9,) and near9[0][:4].tolist() == near4[0].tolist()
     assert len(set(near9[0].tolist())) == 9
+
+
+def test_empty_observation_list_returns_the_prior():
+    """A window without observations: the reference's loop body never runs (ensrf.py:50) and the posterior is the
+    prior -- inflated first if inflation was requested (assimilation.py:132-134)."""
+    EnsembleState, Observation, EnSRF = _api()
+    case = make_case(ny=19, nx=36, nmem=6, nvars=2, ntimes=1, nobs=3, seed=81)
+    state, _ = build_objects(case, EnsembleState, Observation)
+    prior = state.to_vect().copy()
+    post, obs = EnSRF(state, [], verbose=False, loc='GC').update()
+    assert obs == [] and post is not state
+    np.testing.assert_array_equal(post.to_vect(), prior)
+    np.testing.assert_array_equal(state.to_vect(), prior)
+    post, _ = EnSRF(state, [], inflation=1.5, verbose=False, loc='GC').update()
+    m = prior.mean(axis=1, keepdims=True)
+    np.testing.assert_allclose(post.to_vect(), (prior - m) * 1.5 + m, rtol=1e-14)
+    np.testing.assert_allclose(state.to_vect(), (prior - m) * 1.5 + m, rtol=1e-14)     # inflated in place, as the reference
