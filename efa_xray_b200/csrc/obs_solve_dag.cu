@@ -210,6 +210,7 @@ struct DgArgs {
     int *ticket;
     int *status;                 // != 0: watchdog fired (value = 1 + index of the record that never arrived)
     unsigned long long watchdog_ns;
+    int local_gpu_scope;         // distributed variant: gpu-scope stores for the rank's own copy of a record (EXB_DAG_LOCAL_GPU)
     int hot_poll;                // poll the record itself while waiting for the last predecessor of a batch (EXB_DAG_HOT)
     int64_t nobs, row_begin, row_end;
     int nens, loc_mode;
@@ -546,12 +547,20 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
                     }
                 }
             } else {
-                // own copy first (local readers are the closest in index), then the peers
+                // own copy first (local readers are the closest in index; gpu scope is enough for them), then the peers
                 for (int q = 0; q < a.world; ++q) {
                     const int dst = (a.rank + q) % a.world;
                     unsigned long long *p = reinterpret_cast<unsigned long long *>(static_cast<T *>(a.P_peer[dst]) + (j * 32 + lane) * MC);
                     if (lane * MC < nens) {
-                        if constexpr (NW % 4 == 0) {
+                        if (q == 0 && a.local_gpu_scope) {
+                            if constexpr (NW % 4 == 0) {
+#pragma unroll
+                                for (int c = 0; c < NW; c += 4) dg_st32(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < NW; c += 2) dg_st16(p + c, pw[c], pw[c + 1]);
+                            }
+                        } else if constexpr (NW % 4 == 0) {
 #pragma unroll
                             for (int c = 0; c < NW; c += 4) dg_st32_sys(p + c, pw[c], pw[c + 1], pw[c + 2], pw[c + 3]);
                         } else {
@@ -580,7 +589,8 @@ __global__ void __launch_bounds__(DG_WARPS * 32, DG_MINBLOCKS) dag_solve_kernel(
             } else {
                 for (int q = 0; q < a.world; ++q) {
                     const int dst = (a.rank + q) % a.world;
-                    dg_st16_sys(static_cast<double *>(a.S_peer[dst]) + j * 2, s0w, s1w);
+                    if (q == 0 && a.local_gpu_scope) dg_st16(static_cast<double *>(a.S_peer[dst]) + j * 2, s0w, s1w);
+                    else dg_st16_sys(static_cast<double *>(a.S_peer[dst]) + j * 2, s0w, s1w);
                 }
             }
         }
@@ -848,6 +858,7 @@ int exb_obs_solve_dag(T *Ym, T *Yp, const double *ob_value, const double *ob_err
         a.status = sd;
         a.watchdog_ns = dg_watchdog_ns(nobs);
         a.hot_poll = dg_hot_poll();
+        a.local_gpu_scope = getenv("EXB_DAG_LOCAL_GPU") ? atoi(getenv("EXB_DAG_LOCAL_GPU")) : 1;
     }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
@@ -898,6 +909,7 @@ static int dg_solve_dist(void *plan, T *Ym, T *Yp, const double *ob_value, const
         a.status = sd;
         a.watchdog_ns = dg_watchdog_ns(nobs);
         a.hot_poll = dg_hot_poll();
+        a.local_gpu_scope = getenv("EXB_DAG_LOCAL_GPU") ? atoi(getenv("EXB_DAG_LOCAL_GPU")) : 1;
     }
     a.Ym = Ym; a.Yp = Yp; a.ob_value = ob_value; a.ob_error = ob_error; a.ob_assim = ob_assim; a.geo = geo; a.rec = rec;
     a.counters = counters; a.off = pl->off; a.list = nullptr; a.list_base = 0; a.P = nullptr; a.S = nullptr;
