@@ -163,6 +163,14 @@ def stencil_search(grid: GridTables, ob_lat, ob_lon, force_general=False, dev_ta
     return idx4, w4, nex
 
 
+def _dist_search_wanted():
+    """EXB_DIST_SEARCH=1: the ranks of a sharded analysis search a slice of the obs each and all-gather the stencils
+    instead of every rank searching all obs.  Verified at N = 2 (identical analysis) but not faster there -- the setup's
+    critical path is the predecessor-list build, not the search -- so it is off by default."""
+    import os
+    return os.environ.get('EXB_DIST_SEARCH', '0') == '1'
+
+
 def pseudo_distance_order(grid: GridTables, lat, lon, npt):
     """Flat indices of the npt grid points with the smallest pseudo-distance to (lat, lon), ordered by (distance,
     flat index): nearest_points for any npt (state/ensemble.py:152-168)."""
@@ -194,8 +202,32 @@ def ob_priors(X, grid: GridTables, obs: ObsArrays, sfx, nlev=None, band=None, gr
                    'row0': torch.as_tensor(np.ascontiguousarray(obs.row0, dtype=np.int64)).to(dev),
                    'row1': torch.as_tensor(np.ascontiguousarray(obs.row1, dtype=np.int64)).to(dev),
                    'tw0': _dev_f64(obs.tw0, dev), 'tw1': _dev_f64(obs.tw1, dev)}
-    idx4, w4, nex = stencil_search(grid, None, None, dev_tables=(obs_dev['lat'], obs_dev['lon'], obs_dev['sinlat'],
-                                                                   obs_dev['coslon']))
+    tables = (obs_dev['lat'], obs_dev['lon'], obs_dev['sinlat'], obs_dev['coslon'])
+    world = 1
+    if band is not None:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            world = dist.get_world_size(group)
+    if world > 1 and obs.nobs >= 64 * world and _dist_search_wanted():
+        # every rank needs the stencils of ALL obs (it gathers the points of its own band), but the search itself is
+        # the same on every rank: each one searches a slice of the obs and the slices are all-gathered (6 MB)
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        chunk = -(-obs.nobs // world)
+        a, b = min(rank * chunk, obs.nobs), min((rank + 1) * chunk, obs.nobs)
+        idx4 = torch.zeros((world * chunk, 4), dtype=torch.int64, device=dev)
+        w4 = torch.zeros((world * chunk, 4), dtype=torch.float64, device=dev)
+        i_mine, w_mine, nex = stencil_search(grid, None, None, dev_tables=tuple(t[a:b] for t in tables))
+        i_pad = torch.zeros((chunk, 4), dtype=torch.int64, device=dev)
+        w_pad = torch.zeros((chunk, 4), dtype=torch.float64, device=dev)
+        i_pad[:b - a].copy_(i_mine)
+        w_pad[:b - a].copy_(w_mine)
+        dist.all_gather_into_tensor(idx4, i_pad, group=group)
+        dist.all_gather_into_tensor(w4, w_pad, group=group)
+        dist.all_reduce(nex, group=group)
+        idx4, w4 = idx4[:obs.nobs].contiguous(), w4[:obs.nobs].contiguous()
+    else:
+        idx4, w4, nex = stencil_search(grid, None, None, dev_tables=tables)
     # 8-point stencil = 4 space points x 2 time levels, re-based to the band's shard (index/weight bookkeeping only)
     y0, y1 = band if band is not None else (0, grid.ny)
     idx8 = torch.empty((obs.nobs, 8), dtype=torch.int64, device=dev)
