@@ -43,38 +43,48 @@ class Assimilation():
                          "defined by the reference (observation/observation.py:82)" % (loc,))
 
     def _obs_arrays(self, loc_mode):
-        """Structure-of-arrays view of self.obs with the forward-operator bookkeeping per ob (one pass over the list
-        per attribute; everything after that is vectorised)."""
+        """Structure-of-arrays view of self.obs with the forward-operator bookkeeping per ob.  One pass over the list
+        (operator.attrgetter pulls the eight attributes of an ob in C); everything after that is vectorised."""
+        from operator import attrgetter
         st = self.prior
         obs = self.obs
         varnames = st.vars()
         nt, ny, nx = st.ntimes(), st.ny(), st.nx()
         n = len(obs)
+        if n:
+            cols = list(zip(*map(attrgetter('value', 'error', 'lat', 'lon', 'obtype', 'time', 'assimilate_this',
+                                            'localize_radius'), obs)))
+        else:
+            cols = [()] * 8
+        value, error, lat, lon, obtype, obtime, flag, radius = cols
         vidx = {v: i for i, v in enumerate(varnames)}
         try:
-            var = np.fromiter((vidx[ob.obtype] for ob in obs), dtype=np.int64, count=n)
+            var = np.fromiter(map(vidx.__getitem__, obtype), dtype=np.int64, count=n)
         except KeyError as e:
             raise KeyError('observation type %s is not a state variable %r' % (e, varnames))
-        times = np.array([ob.time for ob in obs], dtype='datetime64[us]').astype('datetime64[ns]') if n else \
+        # ob times: converting 1e5 datetime objects one by one is slow, and obs usually share a handful of distinct
+        # times -- convert the distinct ones and index
+        uniq = {}
+        codes = np.fromiter((uniq.setdefault(t, len(uniq)) for t in obtime), dtype=np.int64, count=n)
+        utimes = np.array([np.datetime64(t) for t in uniq], dtype='datetime64[ns]') if uniq else \
             np.zeros(0, dtype='datetime64[ns]')
+        times = utimes[codes] if n else np.zeros(0, dtype='datetime64[ns]')
         tlo, thi, wlo, whi, outside = engine.time_weights(st['validtime'].values, times)
         if outside.any():
             print("Interpolation is outside of time range in state!")
             raise ObTimeOutsideState("observation %d (time %s) is outside the state's valid times"
                                      % (int(np.argmax(outside)), obs[int(np.argmax(outside))].time))
-        assim = np.fromiter((1 if ob.assimilate_this else 0 for ob in obs), dtype=np.uint8, count=n)
+        assim = np.fromiter(map(bool, flag), dtype=np.bool_, count=n).astype(np.uint8)
         hw = np.ones(n)
         if loc_mode == engine.LOC_GC:
             # abs(localize_radius) of the obs that will be assimilated: TypeError on None, as observation.py:120
-            radii = [ob.localize_radius if ob.assimilate_this else 1.0 for ob in obs]
+            radii = [r if f else 1.0 for r, f in zip(radius, flag)]
             if any(r is None for r in radii):
                 abs(None)                                # numpy would turn None into NaN silently
             hw = np.abs(np.array(radii, dtype=np.float64))
         return engine.ObsArrays(
-            value=np.fromiter((ob.value for ob in obs), dtype=np.float64, count=n),
-            error=np.fromiter((ob.error for ob in obs), dtype=np.float64, count=n),
-            lat=np.fromiter((ob.lat for ob in obs), dtype=np.float64, count=n),
-            lon=np.fromiter((ob.lon for ob in obs), dtype=np.float64, count=n),
+            value=np.array(value, dtype=np.float64), error=np.array(error, dtype=np.float64),
+            lat=np.array(lat, dtype=np.float64), lon=np.array(lon, dtype=np.float64),
             halfwidth=hw, assimilate=assim,
             row0=(var * nt + tlo) * (ny * nx), row1=(var * nt + thi) * (ny * nx), tw0=wlo, tw1=whi)
 

@@ -66,12 +66,12 @@ class EnSRF(Assimilation):
         pm, pv = res.prior_mean.tolist(), res.prior_var.tolist()
         qm, qv = res.post_mean.tolist(), res.post_var.tolist()
         done = res.assimilated.tolist()
-        for k, ob in enumerate(self.obs):
-            ob.prior_mean = pm[k]
-            ob.prior_var = pv[k]
-            if done[k]:
-                ob.post_mean = qm[k]
-                ob.post_var = qv[k]
+        for ob, a, b, c, d, f in zip(self.obs, pm, pv, qm, qv, done):
+            ob.prior_mean = a
+            ob.prior_var = b
+            if f:
+                ob.post_mean = c
+                ob.post_var = d
                 ob.assimilated = True
             else:
                 ob.assimilated = False
