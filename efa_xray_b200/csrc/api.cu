@@ -426,6 +426,29 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     EXB_CUDA(cudaMemsetAsync(dcnt.p, 0, 8 * sizeof(unsigned long long), st));
     EXB_TRY(exb_grid_unitvec(dlat.as<double>(), dlon.as<double>(), npts, dgu.as<double>(), st));
     EXB_TRY(exb_obs_prepare(ob + 2 * nobs, ob + 3 * nobs, ob + 4 * nobs, nobs, loc_mode, dgeo.as<double>(), st));
+    // The geometry-only parts of the solve (predecessor lists) and of the sweep (candidate lists) are built on side
+    // streams while the ob priors are gathered and the state is uploaded (exb_obs_plan_create, exb_sweep_plan_create).
+    cudaStream_t s_p1 = nullptr, s_p2 = nullptr;
+    EXB_CUDA(cudaStreamCreateWithFlags(&s_p1, cudaStreamNonBlocking));
+    EXB_CUDA(cudaStreamCreateWithFlags(&s_p2, cudaStreamNonBlocking));
+    struct PlanGuard {
+        cudaStream_t a, b;
+        void *oplan = nullptr, *splan = nullptr;
+        ~PlanGuard() {
+            if (oplan) exb_obs_plan_destroy(oplan);
+            if (splan) exb_sweep_plan_destroy(splan);
+            cudaStreamSynchronize(a); cudaStreamSynchronize(b);
+            cudaStreamDestroy(a); cudaStreamDestroy(b);
+        }
+    } plans{s_p1, s_p2};
+    cudaEvent_t ev_geo;
+    EXB_CUDA(cudaEventCreateWithFlags(&ev_geo, cudaEventDisableTiming));
+    struct GeoEvGuard { cudaEvent_t e; ~GeoEvGuard() { cudaEventDestroy(e); } } geguard{ev_geo};
+    EXB_CUDA(cudaEventRecord(ev_geo, st));
+    if (loc_mode == EXB_LOC_GC) {
+        EXB_CUDA(cudaStreamWaitEvent(s_p1, ev_geo, 0));
+        EXB_TRY(exb_obs_plan_create(dgeo.as<double>(), dassim.as<uint8_t>(), nobs, loc_mode, s_p1, &plans.oplan));
+    }
     if (rect)
         EXB_TRY(exb_stencil_search_rect(dsl.as<double>(), dcl.as<double>(), dlaty.as<double>(), dlonx.as<double>(), ny, nx,
                                         ob + 5 * nobs, ob + 6 * nobs, ob + 2 * nobs, ob + 3 * nobs, nobs,
@@ -504,17 +527,33 @@ extern "C" int exb_ensrf_host_f64(double *X_host, int64_t nlev, int64_t ny, int6
     }
     EXB_TRY(exb_split_mean_pert_f64(dY.as<double>(), dYm.as<double>(), nobs, nens, st));
     EXB_CUDA(cudaEventRecord(ev[2], st));
+    if (fused) {
+        // (blocks the host until the plan's counting pass is done -- the device is busy with the gather / uploads)
+        EXB_CUDA(cudaStreamWaitEvent(s_p2, ev_geo, 0));
+        EXB_TRY(exb_sweep_plan_create(dgu.as<double>(), nlev, ny, nx, dgeo.as<double>(), dassim.as<uint8_t>(), nobs, 0, nobs, 0, ny,
+                                      loc_mode, s_p2, &plans.splan));
+    }
 
     // ---- the serial analysis: obs-space solve, then the state band by band ----------------------------------
-    EXB_TRY(exb_obs_solve_f64(dYm.as<double>(), dY.as<double>(), ob + 0 * nobs, ob + 1 * nobs, dassim.as<uint8_t>(),
-                              dgeo.as<double>(), nobs, nens, loc_mode, drec.as<double>(),
-                              dcnt.as<unsigned long long>(), st));
+    if (plans.oplan)
+        EXB_TRY(exb_obs_solve_planned_f64(plans.oplan, dYm.as<double>(), dY.as<double>(), ob + 0 * nobs, ob + 1 * nobs,
+                                          dassim.as<uint8_t>(), dgeo.as<double>(), nobs, nens, loc_mode, drec.as<double>(),
+                                          dcnt.as<unsigned long long>(), st));
+    else
+        EXB_TRY(exb_obs_solve_f64(dYm.as<double>(), dY.as<double>(), ob + 0 * nobs, ob + 1 * nobs, dassim.as<uint8_t>(),
+                                  dgeo.as<double>(), nobs, nens, loc_mode, drec.as<double>(),
+                                  dcnt.as<unsigned long long>(), st));
     if (fused) {
         for (size_t b = 0; b < nbands; ++b) {
             EXB_CUDA(cudaStreamWaitEvent(st, arrived[b], 0));
-            EXB_TRY(exb_state_sweep_f64(dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(), dY.as<double>(), drec.as<double>(),
-                                        dgeo.as<double>(), nobs, 0, nobs, edges[b], edges[b + 1], loc_mode,
-                                        dcnt.as<unsigned long long>(), st));
+            if (plans.splan)
+                EXB_TRY(exb_state_sweep_planned_f64(plans.splan, dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(), dY.as<double>(),
+                                                    drec.as<double>(), dgeo.as<double>(), nobs, 0, nobs, edges[b], edges[b + 1],
+                                                    loc_mode, dcnt.as<unsigned long long>(), st));
+            else
+                EXB_TRY(exb_state_sweep_f64(dX.as<double>(), nlev, ny, nx, nens, dgu.as<double>(), dY.as<double>(), drec.as<double>(),
+                                            dgeo.as<double>(), nobs, 0, nobs, edges[b], edges[b + 1], loc_mode,
+                                            dcnt.as<unsigned long long>(), st));
             EXB_CUDA(cudaEventRecord(swept[b], st));
             // download of the band that finished before this one (pageable destinations block the host here while
             // this band is being swept, pinned ones do not block at all)
