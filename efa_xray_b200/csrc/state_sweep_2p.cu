@@ -34,13 +34,15 @@
 #include <cstdlib>
 #include <cstring>
 
-#define S2_NW 16                       // warps per CTA: four per SM sub-partition, 128 registers per thread
-#define S2_CW 16                       // every warp is a consumer in phase B (a 17th warp would put five warps on one
-                                       // sub-partition's 16 K registers: 96 per thread) and takes turns issuing the copies
-#define S2_NT (S2_NW * 32)
-#define S2_ROWS (S2_CW * 8)            // state rows per CTA
+// Warps per CTA (template parameter NW of the kernel, 128 registers per thread either way):
+//   16  one CTA per SM, four warps per sub-partition, 128 state rows per patch (a 17th warp would put five warps on one
+//       sub-partition's 16 K registers: 96 per thread);
+//    8  two CTAs per SM, 64 rows per patch each: while one CTA is in phase A (scalar FP64) the other can be in phase B
+//       (DMMA).  Measured slower (config 3: 146.9 against 137.4 ms, profiles/r02_sweep.md): the two kinds of work
+//       share the FP64 issue port, so overlapping them gains nothing, and the per-patch work (weights, Gram matrices,
+//       scan) is spread over half as many rows.  EXB_S2_WARPS=8 selects it (kept as a tested variant).
+// Every warp is a consumer in phase B and takes turns issuing the copies.
 #define S2_CAND 2048                   // candidate capacity of a chunk (256 batches)
-#define S2_SCAN (2 * S2_NT)            // list entries per scan step (2 per thread)
 #define S2_MAXSTAGES 16
 
 struct S2Params {
@@ -138,8 +140,11 @@ template <int NT3> __host__ __device__ constexpr int s2_yst() { return ((8 * NT3
 template <int NT3> __host__ __device__ constexpr int s2_ydoubles() { return 8 * s2_yst<NT3>() + 16; }
 
 // Stage layout (doubles): y rows [s2_ydoubles] | block = om[8][G] (ob-major) | Gram[64]
-template <int NT3, typename TS>
-__global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params p) {
+template <int NT3, typename TS, int NW>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) state_sweep_2p_kernel(const S2Params p) {
+    constexpr int NTH = NW * 32;             // threads per CTA
+    constexpr int ROWS = NW * 8;             // state rows per CTA
+    constexpr int SCAN = 2 * NTH;            // list entries per scan step (2 per thread)
     TS *const gXp = static_cast<TS *>(p.Xp);
     TS *const gxm = static_cast<TS *>(p.xm);
     constexpr int YST = s2_yst<NT3>();
@@ -149,15 +154,15 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_ring = reinterpret_cast<double *>(smem_raw);                                   // [nstages][stage_doubles]
-    double *s_gu = s_ring + (size_t)p.nstages * p.stage_doubles;                             // [3][S2_ROWS]
-    double *s_sob = s_gu + 3 * S2_ROWS;                                                      // [S2_NW][8][6]
-    double2 *s_xch = reinterpret_cast<double2 *>(s_sob + S2_NW * 48);                          // [S2_NW][32]
-    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_xch + S2_NW * 32); // [S2_MAXSTAGES]
+    double *s_gu = s_ring + (size_t)p.nstages * p.stage_doubles;                             // [3][ROWS]
+    double *s_sob = s_gu + 3 * ROWS;                                                      // [NW][8][6]
+    double2 *s_xch = reinterpret_cast<double2 *>(s_sob + NW * 48);                          // [NW][32]
+    unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_xch + NW * 32); // [S2_MAXSTAGES]
     unsigned long long *s_empty = s_full + S2_MAXSTAGES;                                      // [S2_MAXSTAGES]
     int *s_cand = reinterpret_cast<int *>(s_empty + S2_MAXSTAGES);                            // [S2_CAND]
-    int *s_gvalid = s_cand + S2_CAND;                                                         // [S2_ROWS]
-    int *s_wcnt = s_gvalid + S2_ROWS;                                                         // [S2_NW]
-    int *s_misc = s_wcnt + S2_NW;                                                             // [4]
+    int *s_gvalid = s_cand + S2_CAND;                                                         // [ROWS]
+    int *s_wcnt = s_gvalid + ROWS;                                                         // [NW]
+    int *s_misc = s_wcnt + NW;                                                             // [4]
     float *s_bound = reinterpret_cast<float *>(s_misc + 4);                                   // [4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
     if (tid == 0) s_misc[0] = p.abort_flag ? *reinterpret_cast<const volatile int *>(p.abort_flag) : 0;
     if (tid < S) {
         s2_mbar_init(s_full + tid, 1);           // the issuer's arrive.expect_tx; the copies complete the bytes
-        s2_mbar_init(s_empty + tid, S2_CW);      // one arrive per consumer warp
+        s2_mbar_init(s_empty + tid, NW);      // one arrive per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -219,25 +224,25 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
             const int cy = min(max(gy, p.y_begin), p.y_end - 1), cx = min(gx, p.nx - 1);
             const int64_t pt = (int64_t)cy * p.nx + cx;
             s_gu[tid] = p.grid_u[pt];
-            s_gu[S2_ROWS + tid] = p.grid_u[p.npts + pt];
-            s_gu[2 * S2_ROWS + tid] = p.grid_u[2 * p.npts + pt];
+            s_gu[ROWS + tid] = p.grid_u[p.npts + pt];
+            s_gu[2 * ROWS + tid] = p.grid_u[2 * p.npts + pt];
             s_gvalid[tid] = ok;
         }
         __syncthreads();
         if (warp == 0) {
             // bounding cap of the patch: centre = normalised sum of its unit vectors, radius = largest angle to a point
             double cx = 0, cy = 0, cz = 0;
-            for (int g = lane; g < G; g += 32) { cx += s_gu[g]; cy += s_gu[S2_ROWS + g]; cz += s_gu[2 * S2_ROWS + g]; }
+            for (int g = lane; g < G; g += 32) { cx += s_gu[g]; cy += s_gu[ROWS + g]; cz += s_gu[2 * ROWS + g]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 cx += __shfl_xor_sync(0xffffffffu, cx, o); cy += __shfl_xor_sync(0xffffffffu, cy, o);
                 cz += __shfl_xor_sync(0xffffffffu, cz, o);
             }
             const double nn = sqrt(cx * cx + cy * cy + cz * cz);
-            if (nn > 1e-12) { cx /= nn; cy /= nn; cz /= nn; } else { cx = s_gu[0]; cy = s_gu[S2_ROWS]; cz = s_gu[2 * S2_ROWS]; }
+            if (nn > 1e-12) { cx /= nn; cy /= nn; cz /= nn; } else { cx = s_gu[0]; cy = s_gu[ROWS]; cz = s_gu[2 * ROWS]; }
             double cmin = 1.0;
             for (int g = lane; g < G; g += 32)
-                cmin = fmin(cmin, cx * s_gu[g] + cy * s_gu[S2_ROWS + g] + cz * s_gu[2 * S2_ROWS + g]);
+                cmin = fmin(cmin, cx * s_gu[g] + cy * s_gu[ROWS + g] + cz * s_gu[2 * ROWS + g]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
             if (lane == 0) {
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
         for (;;) {
             // =============================== PHASE A (1): candidates of this chunk ===============================
             int ncand = 0;
-            while (pos < le && ncand + S2_SCAN <= p.cand_cap) {
+            while (pos < le && ncand + SCAN <= p.cand_cap) {
                 const int64_t e0 = pos + 2 * tid;
                 int i0 = -1, i1 = -1;
                 if (e0 < le) i0 = list ? __ldg(list + e0) : (int)e0;
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 __syncthreads();
                 int base = ncand, total = 0;
 #pragma unroll
-                for (int w = 0; w < S2_NW; ++w) {
+                for (int w = 0; w < NW; ++w) {
                     const int v = s_wcnt[w];
                     if (w < warp) base += v;
                     total += v;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 if (h0) s_cand[o++] = i0;
                 if (h1) s_cand[o] = i1;
                 ncand += total;
-                pos += S2_SCAN;
+                pos += SCAN;
                 __syncthreads();
             }
             S2_TICK(1);
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
             // the consumers' rows are parked while the registers are needed for the weights
             if (loaded) {
 #pragma unroll
-                for (int i = 0; i < 2 * NT3; ++i) xsave[(size_t)i * S2_NT + tid] = x[i];
+                for (int i = 0; i < 2 * NT3; ++i) xsave[(size_t)i * NTH + tid] = x[i];
             }
 
             // =============================== PHASE A (2): one block per batch ===============================
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 double *stg = s_ring + (size_t)warp * (8 * YW);
                 // (measured: staging costs 1.7 % of the kernel more than loading the operands straight from L2 after the
                 // weights, EXB_S2_DEBUG=1 switches it on)
-                const bool stage_rows = (size_t)S2_NW * 8 * YW <= (size_t)S * SD && (p.dbg & 1);
+                const bool stage_rows = (size_t)NW * 8 * YW <= (size_t)S * SD && (p.dbg & 1);
                 // scalars of the obs of a batch, held by lanes 0..7; loaded one batch ahead
                 struct ObSc { double ux, uy, uz, ihw, amax, c1, beta; int kk; };      // (no arithmetic on the loaded values
                                                                                      // here: it would wait for them)
@@ -360,9 +365,9 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                 };
                 ObSc cur, nxt;
                 load_sc(warp, cur);
-                for (int b = warp; b < nb; b += S2_NW) {
+                for (int b = warp; b < nb; b += NW) {
                     const int nq = min(8, ncand - 8 * b);
-                    load_sc(b + S2_NW, nxt);
+                    load_sc(b + NW, nxt);
                     __syncwarp();                                    // the previous batch's readers of sob / stg are done
                     if (lane < 8) {          // per ob: ux uy uz 1/halfwidth a_max beta*c1
                         *reinterpret_cast<double2 *>(sob + 6 * lane) = make_double2(cur.ux, cur.uy);
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     const int nfull = (p.dbg & 2) ? 0 : (G >> 5), R = (p.dbg & 2) ? 0 : (G & 31);
                     for (int sl = 0; sl < nfull; ++sl) {
                         const int gg = lane + 32 * sl;
-                        const double gx = s_gu[gg], gy = s_gu[S2_ROWS + gg], gz = s_gu[2 * S2_ROWS + gg];
+                        const double gx = s_gu[gg], gy = s_gu[ROWS + gg], gz = s_gu[2 * ROWS + gg];
                         const bool gval = s_gvalid[gg] != 0;
 #pragma unroll 2
                         for (int q = 0; q < 8; ++q) gblk[q * G + gg] = weigh(gx, gy, gz, q, gval && q < nq);
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                             const int i = lane + 32 * it, ic = min(i, npr - 1);
                             const int q = (int)(((unsigned)ic * rdiv) >> 20);
                             const int gg = g0 + ic - q * R;
-                            const double w = weigh(s_gu[gg], s_gu[S2_ROWS + gg], s_gu[2 * S2_ROWS + gg], q,
+                            const double w = weigh(s_gu[gg], s_gu[ROWS + gg], s_gu[2 * ROWS + gg], q,
                                                    i < npr && q < nq && s_gvalid[gg] != 0);
                             if (i < npr) gblk[q * G + gg] = w;
                         }
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     loaded = true;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 2 * NT3; ++i) x[i] = xsave[(size_t)i * S2_NT + tid];
+                    for (int i = 0; i < 2 * NT3; ++i) x[i] = xsave[(size_t)i * NTH + tid];
                 }
             }
 
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     }
                     if (lane == 0) s2_mbar_arrive_expect_tx(s_full + st, 8u * ROW_BYTES + blk_bytes);
                 };
-                if (warp < S && warp < nb) issue(warp);
+                for (int j = warp; j < S && j < nb; j += NW) issue(j);
                 int rs = (int)(gbatch % (unsigned)S);
                 unsigned rpar = (gbatch / (unsigned)S) & 1u;
                 for (int b = 0; b < nb; ++b) {
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(S2_NT, 1) state_sweep_2p_kernel(const S2Params
                     rpar ^= (rs == 0) ? 1u : 0u;
                     // this warp's turn to refill a stage?
                     const int j = b - D + S;
-                    if (b >= D && j < nb && ((b - D) & (S2_NW - 1)) == warp) issue(j);
+                    if (b >= D && j < nb && ((b - D) & (NW - 1)) == warp) issue(j);
                 }
                 gbatch += (unsigned)nb;
             }
@@ -688,9 +693,16 @@ __global__ void sweep_rows_kernel(const TS *__restrict__ Yp, const double *__res
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// (read per call: a sweep plan made for the other patch shape is ignored by s2_launch, which then builds its own lists)
+static int s2_warps() {
+    const char *e = getenv("EXB_S2_WARPS");
+    return (e && atoi(e) == 8) ? 8 : 16;
+}
+
 void s2_patch_shape(int64_t nlev, int64_t ny, int64_t nx, int *Lc_out, int *bty_out, int *btx_out) {
-    const int Lc = nlev < S2_ROWS ? (int)nlev : S2_ROWS;
-    const int G = S2_ROWS / Lc;
+    const int rows = 8 * s2_warps();
+    const int Lc = nlev < rows ? (int)nlev : rows;
+    const int G = rows / Lc;
     int bty = 1, btx = G;
     for (int ty = 1; ty * ty <= G; ++ty) {
         const int tx = G / ty;
@@ -701,8 +713,9 @@ void s2_patch_shape(int64_t nlev, int64_t ny, int64_t nx, int *Lc_out, int *bty_
     *Lc_out = Lc; *bty_out = bty; *btx_out = btx;
 }
 
-template <int NT3, typename TS>
+template <int NT3, typename TS, int NW>
 static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepPlan *plan) {
+    constexpr int NTH = NW * 32, ROWS = NW * 8, PER_SM = 16 / NW;
     int Lc, bty, btx;
     s2_patch_shape(p.nlev, p.ny, p.nx, &Lc, &bty, &btx);
     p.ty = bty; p.tx = btx; p.G = bty * btx; p.Lc = Lc;
@@ -718,14 +731,16 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
     EXB_CUDA(cudaGetDevice(&dev));
     EXB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     EXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t fixed = sizeof(double) * (3 * S2_ROWS + S2_NW * 48 + S2_NW * 64) + sizeof(unsigned long long) * 2 * S2_MAXSTAGES +
-                         sizeof(int) * (S2_CAND + S2_ROWS + S2_NW + 4) + sizeof(float) * 4 + 128;
-    int S = (int)(((size_t)max_smem - 1024 - fixed) / (sizeof(double) * p.stage_doubles));
+    const size_t fixed = sizeof(double) * (3 * ROWS + NW * 48 + NW * 64) + sizeof(unsigned long long) * 2 * S2_MAXSTAGES +
+                         sizeof(int) * (S2_CAND + ROWS + NW + 4) + sizeof(float) * 4 + 128;
+    // shared memory of the SM = the largest opt-in block + 1 KB reserved per resident CTA
+    const size_t budget = PER_SM == 1 ? (size_t)max_smem - 1024 : ((size_t)max_smem + 1024) / PER_SM - 1024 - 256;
+    int S = (int)((budget - fixed) / (sizeof(double) * p.stage_doubles));
     if (S > S2_MAXSTAGES) S = S2_MAXSTAGES;
     if (S < 4) return EXB_ERR_UNSUPPORTED;
     p.nstages = S;
     const size_t smem = fixed + sizeof(double) * (size_t)S * p.stage_doubles;
-    EXB_CUDA(cudaFuncSetAttribute(state_sweep_2p_kernel<NT3, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EXB_CUDA(cudaFuncSetAttribute(state_sweep_2p_kernel<NT3, TS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int64_t npatches = (int64_t)p.ntx * p.npr * p.nlc;
     if (npatches >= 0x7fffffff) {
@@ -734,7 +749,7 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
     }
     if (npatches <= 0) return EXB_OK;
     p.npatches = (int)npatches;
-    const int grid = npatches < sms ? (int)npatches : sms;
+    const int grid = npatches < (int64_t)sms * PER_SM ? (int)npatches : sms * PER_SM;
 
     // candidate lists per coarse tile (localised runs only; the kernel walks the ob range otherwise)
     SweepLists lists;
@@ -760,7 +775,7 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
     constexpr int YW = 8 * NT3;
     double *Yw = nullptr, *scratch = nullptr;
     int *ticket = nullptr;
-    p.scratch_stride = (int64_t)(S2_CAND / 8) * p.blk_doubles + (int64_t)2 * NT3 * S2_NT;
+    p.scratch_stride = (int64_t)(S2_CAND / 8) * p.blk_doubles + (int64_t)2 * NT3 * NTH;
     cudaError_t e = exb_malloc_async(&Yw, sizeof(double) * (size_t)(p.nobs + 1) * YW, st);
     if (e == cudaSuccess) e = exb_malloc_async(&scratch, sizeof(double) * (size_t)p.scratch_stride * grid, st);
     if (e == cudaSuccess) e = exb_malloc_async(&ticket, sizeof(int), st);
@@ -780,9 +795,9 @@ static int s2_launch(S2Params &p, const TS *Yp, cudaStream_t st, const ExbSweepP
         }
         p.prof = prof;
         p.dbg = getenv("EXB_S2_DEBUG") ? atoi(getenv("EXB_S2_DEBUG")) : 0;
-        p.cand_cap = S2_CAND;
-        if (const char *e = getenv("EXB_S2_CAP")) { const int v = atoi(e); if (v >= S2_SCAN && v <= S2_CAND) p.cand_cap = v; }
-        state_sweep_2p_kernel<NT3, TS><<<(unsigned)grid, S2_NT, smem, st>>>(p);
+        p.cand_cap = S2_CAND / PER_SM;          // (same scratch area per SM)
+        if (const char *e = getenv("EXB_S2_CAP")) { const int v = atoi(e); if (v >= 2 * NTH && v <= S2_CAND) p.cand_cap = v; }
+        state_sweep_2p_kernel<NT3, TS, NW><<<(unsigned)grid, NTH, smem, st>>>(p);
         exb_count_launches(2);
         rc = exb_check_launch("state_sweep_2p_kernel");
         if (prof) {
@@ -822,10 +837,17 @@ int exb_state_sweep_2p(TS *xm, TS *Xp, int64_t nlev, int64_t ny, int64_t nx, int
     p.y_begin = (int)y_begin; p.y_end = (int)y_end;
     p.kloc = exb_loc_const();
     const int need = (nens + 1 + 7) / 8;            // 8-member tiles incl. the pseudo-member
-    if (need <= 4) return s2_launch<4, TS>(p, Yp, st, plan);
-    if (need <= 7) return s2_launch<7, TS>(p, Yp, st, plan);
-    if (need <= 10) return s2_launch<10, TS>(p, Yp, st, plan);
-    if (need <= 13) return s2_launch<13, TS>(p, Yp, st, plan);
+    if (s2_warps() == 8) {
+        if (need <= 4) return s2_launch<4, TS, 8>(p, Yp, st, plan);
+        if (need <= 7) return s2_launch<7, TS, 8>(p, Yp, st, plan);
+        if (need <= 10) return s2_launch<10, TS, 8>(p, Yp, st, plan);
+        if (need <= 13) return s2_launch<13, TS, 8>(p, Yp, st, plan);
+        return EXB_ERR_UNSUPPORTED;
+    }
+    if (need <= 4) return s2_launch<4, TS, 16>(p, Yp, st, plan);
+    if (need <= 7) return s2_launch<7, TS, 16>(p, Yp, st, plan);
+    if (need <= 10) return s2_launch<10, TS, 16>(p, Yp, st, plan);
+    if (need <= 13) return s2_launch<13, TS, 16>(p, Yp, st, plan);
     return EXB_ERR_UNSUPPORTED;                       // larger ensembles: state_update_mma.cu / state_update.cu
 }
 
