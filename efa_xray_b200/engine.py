@@ -11,6 +11,7 @@ Sequence (reference: assimilation/ensrf.py:33-151, assimilation/assimilation.py:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -602,6 +603,10 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             Ym = torch.empty(obs.nobs, dtype=X.dtype, device=dev)
             _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(Yp), _lib.ptr(Ym), obs.nobs, nens, _lib.stream_ptr())
             tm.mark('setup_ob_priors')
+            lists_first = os.environ.get('EXB_PLAN_ORDER', '1') != '0'
+            if plan is not None and lists_first:
+                # the solve is next on the critical path: its lists are filled before the sweep's plan is started
+                plan.finish()
             if fused and sweep_plan_wanted():
                 # candidate lists of the sweep: geometry only as well, built on another side stream.  Creating the plan
                 # blocks the host until its counting pass is done, so it comes after the ob priors have been enqueued
@@ -610,7 +615,7 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
             if not fused:
                 xm = torch.empty(nrows, dtype=X.dtype, device=dev)
                 _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
-            if plan is not None:
+            if plan is not None and not lists_first:
                 plan.finish()
             tm.mark('setup_plans')
             rec = torch.empty((8, obs.nobs), dtype=torch.float64, device=dev)
