@@ -321,9 +321,15 @@ class ObsPlan:
 
 class SweepPlan:
     """The geometry-only part of the fused state sweep (scan records of the obs, candidate lists per coarse tile),
-    built on a side stream while the ob priors and the obs-space solve are computed (exb_sweep_plan_create)."""
+    built on a side stream while the ob priors and the obs-space solve are computed (exb_sweep_plan_create).
 
-    def __init__(self, grid_u, nlev, ny, nx, obs_dev, geo, nobs, loc_mode, y_begin=0, y_end=None):
+    `after`: an event on the current stream after which grid_u, geo and the ob arrays are valid (default: everything
+    enqueued on the current stream so far).  background=True makes the call from a helper thread: creating the plan
+    blocks its caller until the counting pass is done (the list is sized on the host), and the thread that enqueues
+    the obs-space solve should not wait for that.  wait() joins it; the sweep needs the handle."""
+
+    def __init__(self, grid_u, nlev, ny, nx, obs_dev, geo, nobs, loc_mode, y_begin=0, y_end=None, after=None,
+                 background=False):
         torch = _torch()
         self.handle = C.c_void_p()
         self.grid_u, self.geo = grid_u, geo          # keep the inputs alive and identical to what the sweep is given
@@ -331,12 +337,47 @@ class SweepPlan:
         ready = obs_dev.get('_ready')
         if ready is not None:
             self.stream.wait_event(ready)
-        self.stream.wait_stream(torch.cuda.current_stream())
-        _lib.call('exb_sweep_plan_create', _lib.ptr(grid_u), nlev, ny, nx, _lib.ptr(geo), _lib.ptr(obs_dev['assimilate']), nobs,
-                  0, nobs, y_begin, ny if y_end is None else y_end, loc_mode, C.c_void_p(self.stream.cuda_stream),
-                  C.byref(self.handle))
+        if after is not None:
+            self.stream.wait_event(after)
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream())
+        self._thread, self._exc = None, None
+        assim = obs_dev['assimilate']
+
+        def create():
+            _lib.call('exb_sweep_plan_create', _lib.ptr(grid_u), nlev, ny, nx, _lib.ptr(geo), _lib.ptr(assim), nobs,
+                      0, nobs, y_begin, ny if y_end is None else y_end, loc_mode, C.c_void_p(self.stream.cuda_stream),
+                      C.byref(self.handle))
+
+        if not background:
+            create()
+            return
+
+        def work():
+            try:
+                with torch.cuda.device(geo.device):       # the current device is a per-thread setting
+                    create()
+            except BaseException as e:                   # re-raised by wait()
+                self._exc = e
+
+        import threading
+        self._thread = threading.Thread(target=work, name='exb-sweep-plan', daemon=True)
+        self._thread.start()
+
+    def wait(self):
+        t, self._thread = self._thread, None
+        if t is not None:
+            t.join()
+        e, self._exc = self._exc, None
+        if e is not None:
+            raise e
+        return self
 
     def destroy(self):
+        try:
+            self.wait()
+        except BaseException:
+            pass
         if self.handle:
             _lib.call('exb_sweep_plan_destroy', self.handle)
             self.handle = C.c_void_p()
@@ -594,6 +635,14 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 plan = ObsPlan(obs_dev, geo, obs.nobs, loc_mode)
             fused = fused_sweep_available(X.dtype, nens)
             grid_u = grid.u if band is None else grid.u[:, y0 * nx:y1 * nx].contiguous()
+            # EXB_PLAN_THREAD=1: the sweep plan is made from a helper thread (see SweepPlan).  Measured on config 3: the
+            # 1.3 ms this thread no longer waits are given back by a solve that shares the device with the plan's
+            # kernels (164.9 against 165.3 ms per analysis) -- off by default.
+            plan_thread = os.environ.get('EXB_PLAN_THREAD', '0') == '1'
+            ev_geom = None
+            if plan_thread:
+                ev_geom = torch.cuda.Event()
+                ev_geom.record()             # obs arrays, geo and grid_u are valid from here on
             if Y is None:
                 Yp, nex = ob_priors(X, grid, obs, sfx, nlev=nlev, band=band, group=group, obs_dev=obs_dev)
             elif isinstance(Y, tuple):   # (H.x, n_exact) from ob_priors, owned by this call
@@ -609,9 +658,10 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 plan.finish()
             if fused and sweep_plan_wanted():
                 # candidate lists of the sweep: geometry only as well, built on another side stream.  Creating the plan
-                # blocks the host until its counting pass is done, so it comes after the ob priors have been enqueued
+                # blocks its caller until the counting pass is done, so it comes after the ob priors have been enqueued
                 # (the device computes them meanwhile)
-                splan = SweepPlan(grid_u, nlev, ny, nx, obs_dev, geo, obs.nobs, loc_mode)
+                splan = SweepPlan(grid_u, nlev, ny, nx, obs_dev, geo, obs.nobs, loc_mode, after=ev_geom,
+                                  background=plan_thread)
             if not fused:
                 xm = torch.empty(nrows, dtype=X.dtype, device=dev)
                 _lib.call('exb_split_mean_pert_' + sfx, _lib.ptr(X), _lib.ptr(xm), nrows, nens, _lib.stream_ptr())
@@ -634,6 +684,8 @@ def analysis_device(X, nlev, grid: GridTables, obs: ObsArrays, loc_mode, inflati
                 obs_solve(Ym, Yp, obs_dev, geo, nens, loc_mode, rec, counters, sfx, plan=plan)
             tm.mark('obs_solve')
             if fused:
+                if splan is not None:
+                    splan.wait()
                 for ya, yb in (sweep_bands or [(0, ny)]):
                     if before_band is not None:
                         before_band(ya, yb)
