@@ -672,22 +672,31 @@ __global__ void sweep_tile_list_kernel(const float4 *__restrict__ caps, int ntil
     int64_t pos = FILL ? off[t] : 0;
     int count = 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int64_t base = ob_begin; base < ob_end; base += 32) {
-        const int64_t k = base + lane;
-        bool hit = false;
-        if (k < ob_end) {
-            const float4 sc = __ldg(scan + k);
-            if (sc.w >= 0.f) {
-                const float ang = sc.w + cap.w;
-                hit = (ang >= 3.1405f) || (sc.x * cap.x + sc.y * cap.y + sc.z * cap.z >= __cosf(ang) - 4e-6f);
-            }
+    // One warp walks all obs for its tile: the loop is bound by the latency of the scan-record loads, so the records of
+    // TL_UNROLL groups of 32 obs are fetched before the first of them is tested (the groups are still taken in order).
+    constexpr int TL_UNROLL = 8;
+    for (int64_t base = ob_begin; base < ob_end; base += 32 * TL_UNROLL) {
+        float4 sc[TL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < TL_UNROLL; ++u) {
+            const int64_t k = base + 32 * u + lane;
+            sc[u] = (k < ob_end) ? __ldg(scan + k) : make_float4(0.f, 0.f, 0.f, -1.f);
         }
-        if (FILL) {
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (hit) list[pos + __popc(b & lt)] = (int)k;
-            pos += __popc(b);
-        } else {
-            count += hit ? 1 : 0;
+#pragma unroll
+        for (int u = 0; u < TL_UNROLL; ++u) {
+            const int64_t k = base + 32 * u + lane;
+            bool hit = false;
+            if (sc[u].w >= 0.f) {                  // (past the end of the range: w = -1)
+                const float ang = sc[u].w + cap.w;
+                hit = (ang >= 3.1405f) || (sc[u].x * cap.x + sc[u].y * cap.y + sc[u].z * cap.z >= __cosf(ang) - 4e-6f);
+            }
+            if (FILL) {
+                const unsigned b = __ballot_sync(0xffffffffu, hit);
+                if (hit) list[pos + __popc(b & lt)] = (int)k;
+                pos += __popc(b);
+            } else {
+                count += hit ? 1 : 0;
+            }
         }
     }
     if (!FILL) {
